@@ -1,0 +1,125 @@
+#include "gemm.h"
+
+#include "../../include/effocr_b200.h"
+#include "gemm_sm100.cuh"
+
+namespace effocr {
+
+int choose_block_n(int N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N % 256 == 0) return 256;
+  if (N % 192 == 0) return 192;
+  if (N % 128 == 0) return 128;
+  // ragged N: least padding wins, ties to the wider tile
+  int best = 256, best_pad = (256 - N % 256) % 256;
+  const int cands[3] = {192, 128, 64};
+  for (int c : cands) {
+    int pad = (c - N % c) % c;
+    if (pad < best_pad) { best = c; best_pad = pad; }
+  }
+  return best;
+}
+
+template <int BN, class Epi>
+static int launch(const GemmArgs& a, const typename Epi::Params& ep, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN));
+  auto kern = gemm_tn_kernel<BN, Epi>;
+  static bool attr_done = false;  // per instantiation
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a.M, a.N, a.K, ep);
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+template <class Epi>
+static int launch_bn(int bn, const GemmArgs& a, const typename Epi::Params& ep, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch<64, Epi>(a, ep, stream);
+    case 128: return launch<128, Epi>(a, ep, stream);
+    case 192: return launch<192, Epi>(a, ep, stream);
+    case 256: return launch<256, Epi>(a, ep, stream);
+  }
+  return fail(EFFOCR_ERR_INVALID, "block_n must be 64, 128, 192 or 256");
+}
+
+template <int ACT, typename OutT, bool RES>
+static int launch_store(int bn, const GemmArgs& a, cudaStream_t stream) {
+  using Epi = EpiStore<ACT, OutT, RES>;
+  typename Epi::Params ep;
+  ep.out = reinterpret_cast<OutT*>(a.out);
+  ep.ldo = a.ldo;
+  ep.bias = a.bias;
+  ep.gamma = a.gamma;
+  ep.resid = reinterpret_cast<const OutT*>(a.resid);
+  ep.ldr = a.ldr;
+  return launch_bn<Epi>(bn, a, ep, stream);
+}
+
+int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return fail(EFFOCR_ERR_INVALID, "gemm: empty problem");
+  if (!a.A || !a.W || !a.out) return fail(EFFOCR_ERR_INVALID, "gemm: null operand");
+  if (a.K % 8 != 0 || a.lda % 8 != 0 || a.ldw % 8 != 0)
+    return fail(EFFOCR_ERR_INVALID, "gemm: K and leading dimensions must be multiples of 8 (16-byte TMA pitch)");
+  const int esz = a.out_f32 ? 4 : 2;
+  if ((a.ldo * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.out) & 15) != 0)
+    return fail(EFFOCR_ERR_INVALID, "gemm: output must be 16-byte aligned with a 16-byte multiple pitch");
+  if (a.resid && ((a.ldr * esz) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.resid) & 15) != 0))
+    return fail(EFFOCR_ERR_INVALID, "gemm: residual must be 16-byte aligned with a 16-byte multiple pitch");
+  if ((a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) || (a.gamma && (reinterpret_cast<uintptr_t>(a.gamma) & 15)))
+    return fail(EFFOCR_ERR_INVALID, "gemm: bias / gamma must be 16-byte aligned");
+  const int bn = a.block_n ? a.block_n : choose_block_n(a.N);
+
+  if (a.pos) {
+    if (a.N % 32 != 0 || a.patches <= 0 || !a.bias || !a.out_f32)
+      return fail(EFFOCR_ERR_INVALID, "gemm: patch-embed epilogue needs N % 32 == 0, bias and fp32 output");
+    EpiPatchEmbed::Params ep;
+    ep.x = reinterpret_cast<float*>(a.out);
+    ep.bias = a.bias;
+    ep.pos = a.pos;
+    ep.patches = a.patches;
+    return launch_bn<EpiPatchEmbed>(bn, a, ep, stream);
+  }
+  const bool res = a.resid != nullptr;
+  if (a.out_f32) {
+    if (a.act != ACT_NONE) return fail(EFFOCR_ERR_INVALID, "gemm: fp32 output supports act=none only");
+    return res ? launch_store<ACT_NONE, float, true>(bn, a, stream) : launch_store<ACT_NONE, float, false>(bn, a, stream);
+  }
+  switch (a.act) {
+    case ACT_NONE:
+      return res ? launch_store<ACT_NONE, __half, true>(bn, a, stream)
+                 : launch_store<ACT_NONE, __half, false>(bn, a, stream);
+    case ACT_GELU:
+      if (res) break;
+      return launch_store<ACT_GELU, __half, false>(bn, a, stream);
+    case ACT_SILU:
+      return res ? launch_store<ACT_SILU, __half, true>(bn, a, stream)
+                 : launch_store<ACT_SILU, __half, false>(bn, a, stream);
+  }
+  return fail(EFFOCR_ERR_INVALID, "gemm: unsupported activation / residual combination");
+}
+
+}  // namespace effocr
+
+extern "C" int effocr_gemm_f16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
+                               const float* bias, const float* gamma, const void* resid, long long ldr, void* out,
+                               long long ldo, int act, int out_f32, int block_n, void* stream) {
+  EFFOCR_TRY(effocr::require_sm100());
+  effocr::GemmArgs a;
+  a.A = reinterpret_cast<const __half*>(A);
+  a.lda = lda;
+  a.W = reinterpret_cast<const __half*>(W);
+  a.ldw = ldw;
+  a.M = M; a.N = N; a.K = K;
+  a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr;
+  a.out = out; a.ldo = ldo; a.act = act; a.out_f32 = out_f32; a.block_n = block_n;
+  return effocr::gemm_f16(a, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,48 @@
+// Host-side plumbing shared by the C-ABI translation units: error reporting, TMA tensor-map
+// encoding (driver entry point fetched through the runtime, so the library links only cudart
+// and still dlopen()s on a machine without a GPU), device properties.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace effocr {
+
+enum : int {
+  EFFOCR_OK = 0,
+  EFFOCR_ERR_INVALID = 1,   // bad argument
+  EFFOCR_ERR_CUDA = 2,      // CUDA runtime / driver failure
+  EFFOCR_ERR_NO_DEVICE = 3, // not an sm_100 device
+  EFFOCR_ERR_NOMEM = 4,
+};
+
+void set_last_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define EFFOCR_CUDA(expr)                                          \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return ::effocr::cuda_fail(_e, #expr);  \
+  } while (0)
+
+#define EFFOCR_TRY(expr)          \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != 0) return _s;       \
+  } while (0)
+
+// Number of SMs on the current device (148 on B200); cached per device.
+int sm_count();
+// Fails loudly unless the current device is compute capability 10.x.
+int require_sm100();
+
+// 2-D row-major fp16 tensor [rows, cols] with leading dimension ld (elements), tiled in
+// boxes of box_rows x 64 columns, 128-byte swizzle, out-of-bounds reads return zero.
+int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows);
+
+}  // namespace effocr
