@@ -35,6 +35,23 @@ SIGNATURES = {
     "effocr_device_ok": (c_int, []),
     "effocr_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "effocr_vit_destroy": (None, [c_void_p]),
+    "effocr_vit_embed_dim": (c_int, [c_void_p]),
+    "effocr_vit_max_batch": (c_int, [c_void_p]),
+    "effocr_vit_patch_buffer": (c_void_p, [c_void_p]),
+    "effocr_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_int,
+                                 c_void_p]),
+    "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "effocr_l2_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "effocr_knn_create": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "effocr_knn_destroy": (None, [c_void_p]),
+    "effocr_knn_ntotal": (c_int, [c_void_p]),
+    "effocr_knn_dim": (c_int, [c_void_p]),
+    "effocr_knn_vectors": (c_void_p, [c_void_p]),
+    "effocr_knn_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

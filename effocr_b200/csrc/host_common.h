@@ -9,15 +9,10 @@
 
 #include <string>
 
+#include "../../include/effocr_b200.h"
+
 namespace effocr {
 
-enum : int {
-  EFFOCR_OK = 0,
-  EFFOCR_ERR_INVALID = 1,   // bad argument
-  EFFOCR_ERR_CUDA = 2,      // CUDA runtime / driver failure
-  EFFOCR_ERR_NO_DEVICE = 3, // not an sm_100 device
-  EFFOCR_ERR_NOMEM = 4,
-};
 
 void set_last_error(const std::string& msg);
 int fail(int code, const std::string& msg);

@@ -1,0 +1,245 @@
+// ViT recognizer encoder (timm vit_{tiny,small,base}_patch16_224, num_classes=0) as a C-ABI handle.
+// Replaces `timm.create_model(...)(x)` reached from /root/reference/models/encoders.py:62-64
+// (infer_effocr.py:314) and the ORT session of onnx_engines/recognizer_engine.py:23-27.
+//
+// Numerics: fp16 GEMM operands, fp32 accumulation (TMEM), fp32 residual stream, fp32 LayerNorm /
+// softmax statistics -- SURVEY.md section 0.5 (bf16 or an fp16 residual flips top-1 ids).
+#include <vector>
+
+#include "../../include/effocr_b200.h"
+#include "gemm.h"
+#include "vit_kernels.cuh"
+
+namespace effocr {
+
+struct VitLayer {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  __half *w_qkv, *w_proj, *w_fc1, *w_fc2;
+  float *b_qkv, *b_proj, *b_fc1, *b_fc2;
+};
+
+struct VitHandle {
+  int D = 0, H = 0, depth = 0, mlp = 0, max_batch = 0;
+  static constexpr int T = 197, P = 196, PK = 768;
+  __half* w_patch = nullptr;
+  float *b_patch = nullptr, *cls = nullptr, *pos = nullptr, *lnf_w = nullptr, *lnf_b = nullptr;
+  std::vector<VitLayer> layers;
+  // workspace, sized for max_batch
+  __half *patches = nullptr, *h16 = nullptr, *qkv = nullptr, *att = nullptr, *mid = nullptr;
+  float* x = nullptr;
+  std::vector<void*> allocs;
+
+  ~VitHandle() {
+    for (void* p : allocs) cudaFree(p);
+  }
+  template <typename T_>
+  int alloc(T_** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T_));
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    allocs.push_back(q);
+    *p = reinterpret_cast<T_*>(q);
+    return EFFOCR_OK;
+  }
+  int upload_f32(float** dst, const float* src, size_t n) {
+    EFFOCR_TRY(alloc(dst, n));
+    EFFOCR_CUDA(cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    return EFFOCR_OK;
+  }
+  int upload_f16(__half** dst, const float* src, size_t n) {
+    std::vector<__half> tmp(n);
+    for (size_t i = 0; i < n; ++i) tmp[i] = __float2half_rn(src[i]);
+    EFFOCR_TRY(alloc(dst, n));
+    EFFOCR_CUDA(cudaMemcpy(*dst, tmp.data(), n * sizeof(__half), cudaMemcpyHostToDevice));
+    return EFFOCR_OK;
+  }
+};
+
+template <typename OutT>
+static int layernorm_launch(const float* x, long long ldx, const float* g, const float* b, OutT* out, long long ldo,
+                            int rows, int D, float eps, cudaStream_t s) {
+  const int wpb = 8;
+  const int grid = (rows + wpb - 1) / wpb;
+  switch (D) {
+    case 96: layernorm_rows_kernel<96, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
+    case 192: layernorm_rows_kernel<192, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
+    case 384: layernorm_rows_kernel<384, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
+    case 768: layernorm_rows_kernel<768, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
+    default: return fail(EFFOCR_ERR_INVALID, "layernorm: unsupported width (96/192/384/768)");
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+int layernorm_f16(const float* x, long long ldx, const float* g, const float* b, __half* out, long long ldo, int rows,
+                  int D, float eps, cudaStream_t s) {
+  return layernorm_launch<__half>(x, ldx, g, b, out, ldo, rows, D, eps, s);
+}
+int layernorm_f32(const float* x, long long ldx, const float* g, const float* b, float* out, long long ldo, int rows,
+                  int D, float eps, cudaStream_t s) {
+  return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s);
+}
+
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s) {
+  if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
+  static bool attr = false;
+  if (!attr) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(attention_197x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    attr = true;
+  }
+  const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+  attention_197x64_kernel<<<batch * H, kAttnThreads, kAttnSmemBytes, s>>>(qkv, out, T, H, scale_log2e);
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
+  const int D = v->D, T = VitHandle::T;
+  const int M = B * T;
+  GemmArgs g;
+  // patch embedding + bias + position embedding -> token rows 1..196 of x
+  g = GemmArgs();
+  g.A = v->patches; g.lda = VitHandle::PK; g.W = v->w_patch; g.ldw = VitHandle::PK;
+  g.M = B * VitHandle::P; g.N = D; g.K = VitHandle::PK;
+  g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = v->b_patch; g.pos = v->pos; g.patches = VitHandle::P;
+  EFFOCR_TRY(gemm_f16(g, s));
+  cls_pos_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(v->x, v->cls, v->pos, B, T, D);
+  EFFOCR_CUDA(cudaGetLastError());
+  for (int l = 0; l < v->depth; ++l) {
+    const VitLayer& L = v->layers[l];
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, 1e-6f, s));
+    g = GemmArgs();
+    g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+    g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv;
+    EFFOCR_TRY(gemm_f16(g, s));
+    EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
+    g = GemmArgs();
+    g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D;
+    EFFOCR_TRY(gemm_f16(g, s));
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, 1e-6f, s));
+    g = GemmArgs();
+    g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = M; g.N = v->mlp; g.K = D;
+    g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1;
+    EFFOCR_TRY(gemm_f16(g, s));
+    g = GemmArgs();
+    g.A = v->mid; g.lda = v->mlp; g.W = L.w_fc2; g.ldw = v->mlp; g.M = M; g.N = D; g.K = v->mlp;
+    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_fc2; g.resid = v->x; g.ldr = D;
+    EFFOCR_TRY(gemm_f16(g, s));
+  }
+  // final LayerNorm on the CLS rows only (row stride T * D)
+  EFFOCR_TRY(layernorm_f32(v->x, static_cast<long long>(T) * D, v->lnf_w, v->lnf_b, emb, D, B, D, 1e-6f, s));
+  return EFFOCR_OK;
+}
+
+}  // namespace effocr
+
+using namespace effocr;
+
+extern "C" int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch,
+                                 const float* const* h_weights, int n_weights, effocr_vit_t* out) {
+  if (!out) return fail(EFFOCR_ERR_INVALID, "vit_create: null out");
+  *out = nullptr;
+  EFFOCR_TRY(require_sm100());
+  if (embed_dim != num_heads * 64) return fail(EFFOCR_ERR_INVALID, "vit_create: head dim must be 64");
+  if (embed_dim != 192 && embed_dim != 384 && embed_dim != 768)
+    return fail(EFFOCR_ERR_INVALID, "vit_create: embed dim must be 192, 384 or 768");
+  if (n_weights != 4 + 12 * depth + 2) return fail(EFFOCR_ERR_INVALID, "vit_create: expected 4 + 12*depth + 2 weight tensors");
+  if (max_batch <= 0 || mlp_dim % 8 != 0) return fail(EFFOCR_ERR_INVALID, "vit_create: bad max_batch / mlp_dim");
+  VitHandle* v = new VitHandle();
+  v->D = embed_dim; v->H = num_heads; v->depth = depth; v->mlp = mlp_dim; v->max_batch = max_batch;
+  const int D = embed_dim;
+  int st = EFFOCR_OK;
+  auto W = [&](int i) { return h_weights[i]; };
+  do {
+    if ((st = v->upload_f16(&v->w_patch, W(0), size_t(D) * 768))) break;
+    if ((st = v->upload_f32(&v->b_patch, W(1), D))) break;
+    if ((st = v->upload_f32(&v->cls, W(2), D))) break;
+    if ((st = v->upload_f32(&v->pos, W(3), size_t(197) * D))) break;
+    v->layers.resize(depth);
+    for (int l = 0; l < depth && !st; ++l) {
+      VitLayer& L = v->layers[l];
+      const int o = 4 + 12 * l;
+      if ((st = v->upload_f32(&L.ln1_w, W(o + 0), D))) break;
+      if ((st = v->upload_f32(&L.ln1_b, W(o + 1), D))) break;
+      if ((st = v->upload_f16(&L.w_qkv, W(o + 2), size_t(3) * D * D))) break;
+      if ((st = v->upload_f32(&L.b_qkv, W(o + 3), 3 * D))) break;
+      if ((st = v->upload_f16(&L.w_proj, W(o + 4), size_t(D) * D))) break;
+      if ((st = v->upload_f32(&L.b_proj, W(o + 5), D))) break;
+      if ((st = v->upload_f32(&L.ln2_w, W(o + 6), D))) break;
+      if ((st = v->upload_f32(&L.ln2_b, W(o + 7), D))) break;
+      if ((st = v->upload_f16(&L.w_fc1, W(o + 8), size_t(mlp_dim) * D))) break;
+      if ((st = v->upload_f32(&L.b_fc1, W(o + 9), mlp_dim))) break;
+      if ((st = v->upload_f16(&L.w_fc2, W(o + 10), size_t(D) * mlp_dim))) break;
+      if ((st = v->upload_f32(&L.b_fc2, W(o + 11), D))) break;
+    }
+    if (st) break;
+    if ((st = v->upload_f32(&v->lnf_w, W(4 + 12 * depth), D))) break;
+    if ((st = v->upload_f32(&v->lnf_b, W(5 + 12 * depth), D))) break;
+    const size_t M = size_t(max_batch) * 197;
+    if ((st = v->alloc(&v->patches, size_t(max_batch) * 196 * 768))) break;
+    if ((st = v->alloc(&v->x, M * D))) break;
+    if ((st = v->alloc(&v->h16, M * D))) break;
+    if ((st = v->alloc(&v->qkv, M * 3 * D))) break;
+    if ((st = v->alloc(&v->att, M * D))) break;
+    if ((st = v->alloc(&v->mid, M * mlp_dim))) break;
+  } while (0);
+  if (st) {
+    delete v;
+    return st;
+  }
+  *out = reinterpret_cast<effocr_vit_t>(v);
+  return EFFOCR_OK;
+}
+
+extern "C" void effocr_vit_destroy(effocr_vit_t h) { delete reinterpret_cast<VitHandle*>(h); }
+
+extern "C" int effocr_vit_embed_dim(effocr_vit_t h) { return h ? reinterpret_cast<VitHandle*>(h)->D : 0; }
+extern "C" int effocr_vit_max_batch(effocr_vit_t h) { return h ? reinterpret_cast<VitHandle*>(h)->max_batch : 0; }
+extern "C" void* effocr_vit_patch_buffer(effocr_vit_t h) { return h ? reinterpret_cast<VitHandle*>(h)->patches : nullptr; }
+
+extern "C" int effocr_vit_forward(effocr_vit_t h, const void* d_input, int input_kind, int batch, float* d_emb,
+                                  void* stream) {
+  VitHandle* v = reinterpret_cast<VitHandle*>(h);
+  if (!v || !d_emb || batch < 0) return fail(EFFOCR_ERR_INVALID, "vit_forward: bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (input_kind == EFFOCR_INPUT_PATCH_BUFFER) {
+    if (batch > v->max_batch) return fail(EFFOCR_ERR_INVALID, "vit_forward: batch exceeds max_batch for the in-place patch buffer");
+    return batch == 0 ? EFFOCR_OK : vit_forward_chunk(v, batch, d_emb, s);
+  }
+  if (!d_input) return fail(EFFOCR_ERR_INVALID, "vit_forward: null input");
+  for (int b0 = 0; b0 < batch; b0 += v->max_batch) {
+    const int B = (batch - b0 < v->max_batch) ? batch - b0 : v->max_batch;
+    if (input_kind == EFFOCR_INPUT_NCHW_F32) {
+      const float* img = reinterpret_cast<const float*>(d_input) + size_t(b0) * 3 * 224 * 224;
+      const long long total = static_cast<long long>(B) * 196 * 96;
+      const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+      im2patch_kernel<<<grid, 256, 0, s>>>(img, v->patches, B);
+      EFFOCR_CUDA(cudaGetLastError());
+    } else if (input_kind == EFFOCR_INPUT_PATCH_F16) {
+      const __half* p = reinterpret_cast<const __half*>(d_input) + size_t(b0) * 196 * 768;
+      EFFOCR_CUDA(cudaMemcpyAsync(v->patches, p, size_t(B) * 196 * 768 * 2, cudaMemcpyDeviceToDevice, s));
+    } else {
+      return fail(EFFOCR_ERR_INVALID, "vit_forward: unknown input_kind");
+    }
+    EFFOCR_TRY(vit_forward_chunk(v, B, d_emb + size_t(b0) * v->D, s));
+  }
+  return EFFOCR_OK;
+}
+
+// ---- building-block entry points (unit tests call these through the C ABI)
+extern "C" int effocr_layernorm(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta, void* d_out,
+                                long long ldo, int rows, int dim, float eps, int out_f32, void* stream) {
+  EFFOCR_TRY(require_sm100());
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (rows <= 0) return EFFOCR_OK;
+  return out_f32 ? layernorm_f32(d_x, ldx, d_gamma, d_beta, reinterpret_cast<float*>(d_out), ldo, rows, dim, eps, s)
+                 : layernorm_f16(d_x, ldx, d_gamma, d_beta, reinterpret_cast<__half*>(d_out), ldo, rows, dim, eps, s);
+}
+
+extern "C" int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, void* stream) {
+  EFFOCR_TRY(require_sm100());
+  if (batch <= 0) return EFFOCR_OK;
+  return attention_f16(reinterpret_cast<const __half*>(d_qkv), reinterpret_cast<__half*>(d_out), batch, tokens, heads,
+                       reinterpret_cast<cudaStream_t>(stream));
+}

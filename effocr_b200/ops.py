@@ -1,0 +1,124 @@
+"""Thin torch-tensor wrappers over the C ABI (include/effocr_b200.h).
+
+Every function launches the hand-written sm_100a kernels on the current torch CUDA stream; none
+has a PyTorch or CPU fallback.  Tensors must be CUDA tensors on the current device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+CROP_NCHW_F16, CROP_NCHW_F32, CROP_PATCH_F16 = 0, 1, 2
+INPUT_NCHW_F32, INPUT_PATCH_F16, INPUT_PATCH_BUFFER = 0, 1, 2
+
+IMAGE_DESC_DTYPE = np.dtype([("offset", "<i8"), ("height", "<i4"), ("width", "<i4"), ("pitch", "<i4"),
+                             ("reserved", "<i4")])
+CROP_BOX_DTYPE = np.dtype([("image", "<i4"), ("x0", "<i4"), ("y0", "<i4"), ("x1", "<i4"), ("y1", "<i4")])
+
+
+def _cuda(t: torch.Tensor, dtype=None, name="tensor") -> torch.Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.EffocrError(f"{name} must be a CUDA tensor (effocr_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise _lib.EffocrError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = ACT_NONE, out_dtype=torch.float16, resid=None,
+         gamma=None, out=None, block_n: int = 0) -> torch.Tensor:
+    """out = act(a @ w.T + bias) * gamma + resid, fp16 operands, fp32 accumulate (tcgen05)."""
+    lib = _lib.load()
+    a = _cuda(a, torch.float16, "a")
+    w = _cuda(w, torch.float16, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and a.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        ld = (N + 7) // 8 * 8
+        out = torch.empty((M, ld), device=a.device, dtype=out_dtype)[:, :N]
+    f32 = 1 if out.dtype == torch.float32 else 0
+    _lib.check(lib.effocr_gemm_f16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _lib.ptr(bias),
+                                   _lib.ptr(gamma), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
+                                   out.data_ptr(), out.stride(0), act, f32, block_n, _lib.stream_ptr()), "effocr_gemm_f16")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
+              out_dtype=torch.float16) -> torch.Tensor:
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x")
+    rows, dim = x.shape
+    out = torch.empty((rows, dim), device=x.device, dtype=out_dtype)
+    _lib.check(lib.effocr_layernorm(x.data_ptr(), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), dim,
+                                    rows, dim, eps, 1 if out_dtype == torch.float32 else 0, _lib.stream_ptr()),
+               "effocr_layernorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, batch: int, heads: int) -> torch.Tensor:
+    lib = _lib.load()
+    qkv = _cuda(qkv, torch.float16, "qkv")
+    tokens = qkv.shape[0] // batch
+    out = torch.empty((qkv.shape[0], heads * 64), device=qkv.device, dtype=torch.float16)
+    _lib.check(lib.effocr_attention_f16(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, _lib.stream_ptr()),
+               "effocr_attention_f16")
+    return out
+
+
+def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x").contiguous()
+    out = torch.empty_like(x)
+    _lib.check(lib.effocr_l2_normalize(x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[1], eps, _lib.stream_ptr()),
+               "effocr_l2_normalize")
+    return out
+
+
+def crop_resize(pixels: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor, n_boxes: int, layout: int,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """pixels: u8 device buffer; images/boxes: device byte tensors viewed from IMAGE_DESC_DTYPE /
+    CROP_BOX_DTYPE arrays (see pack_images / pack_boxes)."""
+    lib = _lib.load()
+    pixels = _cuda(pixels, torch.uint8, "pixels")
+    if out is None:
+        if layout == CROP_PATCH_F16:
+            out = torch.empty((n_boxes * 196, 768), device=pixels.device, dtype=torch.float16)
+        else:
+            out = torch.empty((n_boxes, 3, 224, 224), device=pixels.device,
+                              dtype=torch.float32 if layout == CROP_NCHW_F32 else torch.float16)
+    _lib.check(lib.effocr_crop_resize(pixels.data_ptr(), images.data_ptr(), boxes.data_ptr(), n_boxes, layout,
+                                      out.data_ptr(), _lib.stream_ptr()), "effocr_crop_resize")
+    return out
+
+
+def pack_images(arrays, device="cuda", pinned: bool = True):
+    """Concatenate u8 HWC RGB images into one device buffer + descriptor table (one H2D copy each)."""
+    descs = np.zeros(len(arrays), dtype=IMAGE_DESC_DTYPE)
+    off = 0
+    for i, a in enumerate(arrays):
+        assert a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3
+        h, w, _ = a.shape
+        descs[i] = (off, h, w, w * 3, 0)
+        off += (h * w * 3 + 255) // 256 * 256
+    host = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+    hv = host.numpy()
+    for i, a in enumerate(arrays):
+        o = int(descs[i]["offset"])
+        hv[o:o + a.size] = np.ascontiguousarray(a).reshape(-1)
+    pixels = host.to(device, non_blocking=True)
+    images = torch.from_numpy(descs.view(np.uint8).copy()).to(device, non_blocking=True)
+    return pixels, images, descs
+
+
+def pack_boxes(boxes, device="cuda"):
+    """boxes: iterable of (image, x0, y0, x1, y1) integer Python-slice rectangles."""
+    arr = np.asarray(list(boxes), dtype=np.int32).reshape(-1, 5)
+    rec = np.zeros(len(arr), dtype=CROP_BOX_DTYPE)
+    for k, name in enumerate(("image", "x0", "y0", "x1", "y1")):
+        rec[name] = arr[:, k]
+    return torch.from_numpy(rec.view(np.uint8).copy()).to(device, non_blocking=True), len(arr)

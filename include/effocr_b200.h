@@ -56,6 +56,79 @@ EFFOCR_API int effocr_gemm_f16(const void* d_A, long long lda, const void* d_W, 
                     const float* d_bias, const float* d_gamma, const void* d_resid, long long ldr, void* d_out,
                     long long ldo, int act, int out_f32, int block_n, void* stream);
 
+/* ---- K1: fused crop -> square white pad -> AA bilinear 224x224 -> normalise -------------------
+ * Replaces the numpy slice + `create_paired_transform` per-crop CPU path
+ * (infer_effocr.py:284-293, infer_effocr_onnx_multi.py:307-340, utils/datasets_utils.py:69-90,166-172).
+ * `pixels` holds u8 RGB HWC line images; images[i] locates image i inside it; boxes[j] is the
+ * Python slice im[y0:y1, x0:x1] (numpy semantics: negative indices wrap, ends clamp) of image
+ * boxes[j].image.  An empty slice produces an all-zero output crop (the reference's ONNX path feeds
+ * zeros for a failed transform, infer_effocr_onnx_multi.py:151-152,200-204). */
+typedef struct {
+  long long offset; /* byte offset of pixel (0,0) inside `pixels` */
+  int height, width;
+  int pitch;        /* bytes between rows (>= 3 * width) */
+  int reserved;
+} effocr_image_desc;
+typedef struct {
+  int image;
+  int x0, y0, x1, y1;
+} effocr_crop_box;
+#define EFFOCR_CROP_NCHW_F16 0  /* out: fp16 [n, 3, 224, 224] */
+#define EFFOCR_CROP_NCHW_F32 1  /* out: fp32 [n, 3, 224, 224]  (== create_paired_transform output) */
+#define EFFOCR_CROP_PATCH_F16 2 /* out: fp16 [n * 196, 768] patch-major (input of effocr_vit_forward) */
+EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
+                                  const effocr_crop_box* d_boxes, int n_boxes, int layout, void* d_out, void* stream);
+
+/* ---- recognizer encoder: timm vit_{tiny,small,base}_patch16_224, num_classes=0 ----------------
+ * Replaces AutoEncoder.forward (models/encoders.py:62-64, called at infer_effocr.py:314) and
+ * EffRecognizer.run (onnx_engines/recognizer_engine.py:23-27).
+ * h_weights: HOST fp32 tensors in timm layout, in this order (n_weights = 4 + 12*depth + 2):
+ *   patch_embed.proj.weight [D,3,16,16], patch_embed.proj.bias [D], cls_token [D], pos_embed [197,D],
+ *   per block: norm1.weight, norm1.bias, attn.qkv.weight [3D,D], attn.qkv.bias, attn.proj.weight [D,D],
+ *              attn.proj.bias, norm2.weight, norm2.bias, mlp.fc1.weight [4D,D], mlp.fc1.bias,
+ *              mlp.fc2.weight [D,4D], mlp.fc2.bias,
+ *   norm.weight, norm.bias.
+ * The handle owns its weights and a workspace for max_batch crops (larger batches are chunked). */
+typedef struct effocr_vit_s* effocr_vit_t;
+#define EFFOCR_INPUT_NCHW_F32 0     /* d_input: fp32 [B,3,224,224] (the reference's tensor) */
+#define EFFOCR_INPUT_PATCH_F16 1    /* d_input: fp16 [B*196,768] patch-major */
+#define EFFOCR_INPUT_PATCH_BUFFER 2 /* input already written into effocr_vit_patch_buffer(); B <= max_batch */
+EFFOCR_API int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch,
+                                 const float* const* h_weights, int n_weights, effocr_vit_t* out);
+EFFOCR_API void effocr_vit_destroy(effocr_vit_t h);
+EFFOCR_API int effocr_vit_embed_dim(effocr_vit_t h);
+EFFOCR_API int effocr_vit_max_batch(effocr_vit_t h);
+EFFOCR_API void* effocr_vit_patch_buffer(effocr_vit_t h);
+/* d_emb: fp32 [B, D] pooled pre-logits (final-LayerNorm'd CLS token), NOT L2-normalised. */
+EFFOCR_API int effocr_vit_forward(effocr_vit_t h, const void* d_input, int input_kind, int batch, float* d_emb,
+                                  void* stream);
+
+/* building blocks of the encoder, exported for the parity tests */
+EFFOCR_API int effocr_layernorm(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta,
+                                void* d_out, long long ldo, int rows, int dim, float eps, int out_f32, void* stream);
+/* qkv fp16 [B*197, 3*H*64] (rows [q|k|v], each [H,64]) -> out fp16 [B*197, H*64] */
+EFFOCR_API int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, void* stream);
+
+/* ---- a9: row-wise L2 normalisation, x / max(||x||, eps) -------------------------------------
+ * Replaces torch.nn.functional.normalize at infer_effocr.py:316 / infer_effocr_onnx_multi.py:371. */
+EFFOCR_API int effocr_l2_normalize(const float* d_x, float* d_out, int rows, int dim, float eps, void* stream);
+
+/* ---- K10: exact inner-product top-k over a flat index ------------------------------------------
+ * Replaces faiss.IndexFlatIP (add / search) behind pytorch_metric_learning.FaissKNN
+ * (infer_effocr.py:184-187,317; infer_effocr_onnx_multi.py:496-500,372).
+ * create copies d_vectors (fp32 [n, dim], device).  search writes, per query, the k best
+ * (inner product desc, id asc) as fp32 distances and int64 ids; missing results are
+ * (-3.4028235e38, -1) like faiss.  k <= 32.  A handle's search workspace is shared: serialise
+ * concurrent searches on one handle. */
+typedef struct effocr_knn_s* effocr_knn_t;
+EFFOCR_API int effocr_knn_create(const float* d_vectors, int n, int dim, effocr_knn_t* out);
+EFFOCR_API void effocr_knn_destroy(effocr_knn_t h);
+EFFOCR_API int effocr_knn_ntotal(effocr_knn_t h);
+EFFOCR_API int effocr_knn_dim(effocr_knn_t h);
+EFFOCR_API const float* effocr_knn_vectors(effocr_knn_t h);
+EFFOCR_API int effocr_knn_search(effocr_knn_t h, const float* d_queries, int nq, int k, float* d_dist,
+                                 long long* d_idx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,94 @@
+"""GPU parity of the building-block kernels (GEMM epilogues, LayerNorm, attention) through the C ABI,
+against plain fp32 torch on the same inputs.  Tolerances: fp16 operand rounding (rel 2^-11)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K,act,f32,resid,gamma,bn", [
+    (128, 64, 64, 0, 0, False, False, 64),
+    (300, 384, 384, 0, 0, False, False, 0),
+    (1000, 1152, 384, 0, 0, False, False, 0),
+    (1000, 1536, 384, 1, 0, False, False, 0),
+    (1000, 384, 1536, 0, 1, True, False, 0),
+    (777, 384, 384, 0, 1, True, True, 0),
+    (3000, 100, 72, 2, 0, False, False, 0),
+    (4000, 256, 288, 2, 0, True, False, 0),
+    (3000, 21, 512, 0, 1, False, False, 64),
+    (20000, 1152, 384, 0, 0, False, False, 0),   # many tiles per CTA: phase wrap of both pipelines
+])
+def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn):
+    from effocr_b200 import ops
+    torch.manual_seed(0)
+    a = (torch.randn(M, K, device="cuda") * 0.5).half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda")
+    g = torch.randn(N, device="cuda") if gamma else None
+    odt = torch.float32 if f32 else torch.float16
+    ld = (N + 7) // 8 * 8
+    r = torch.randn(M, ld, device="cuda").to(odt)[:, :N] if resid else None
+    out = ops.gemm(a, w, bias=b, act=act, out_dtype=odt, resid=r, gamma=g, block_n=bn)
+    ref = a.float() @ w.float().t() + b
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if act == 2:
+        ref = torch.nn.functional.silu(ref)
+    if gamma:
+        ref = ref * g
+    if resid:
+        ref = ref + r.float()
+    tol = 2e-6 if f32 else 6e-4  # fp32 out: accumulation-order noise only; fp16 out: 2^-11 rounding
+    assert _rel(out, ref) < tol
+    assert torch.isfinite(out.float()).all()
+
+
+def test_gemm_inplace_residual():
+    from effocr_b200 import ops
+    torch.manual_seed(1)
+    M, N, K = 2000, 384, 384
+    a = (torch.randn(M, K, device="cuda") * 0.5).half()
+    w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    x = torch.randn(M, N, device="cuda")
+    ref = x + a.float() @ w.float().t()
+    ops.gemm(a, w, out_dtype=torch.float32, resid=x, out=x)
+    assert _rel(x, ref) < 2e-6
+
+
+@pytest.mark.parametrize("dim", [96, 192, 384, 768])
+@pytest.mark.parametrize("f32", [False, True])
+def test_layernorm(dim, f32):
+    from effocr_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(1003, dim, device="cuda") * 3 + 1
+    g = torch.randn(dim, device="cuda")
+    b = torch.randn(dim, device="cuda")
+    out = ops.layernorm(x, g, b, 1e-6, torch.float32 if f32 else torch.float16)
+    ref = torch.nn.functional.layer_norm(x, (dim,), g, b, 1e-6)
+    assert _rel(out, ref) < (2e-6 if f32 else 4e-4)
+
+
+@pytest.mark.parametrize("batch,heads", [(1, 3), (5, 6), (64, 6)])
+def test_attention(batch, heads):
+    from effocr_b200 import ops
+    torch.manual_seed(0)
+    T, D = 197, heads * 64
+    qkv = (torch.randn(batch * T, 3 * D, device="cuda") * 1.5).half()
+    out = ops.attention(qkv, batch, heads)
+    q, k, v = qkv.float().reshape(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-2, -1) * 0.125).softmax(-1)
+    ref = (att @ v).transpose(1, 2).reshape(batch * T, D)
+    assert _rel(out, ref) < 1.5e-3  # P rounded to fp16 before P.V
+
+
+def test_l2_normalize():
+    from effocr_b200 import ops
+    x = torch.randn(300, 384, device="cuda")
+    x[7] = 0
+    out = ops.l2_normalize(x)
+    ref = torch.nn.functional.normalize(x, p=2, dim=1)
+    assert torch.allclose(out, ref, atol=1e-6, rtol=1e-5)

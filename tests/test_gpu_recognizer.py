@@ -1,0 +1,124 @@
+"""GPU parity of the recognizer path (crop -> ViT -> L2 norm -> kNN) through the C ABI against the
+CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8c):
+  * crop kernel: max-abs <= 1e-3 on the fp16 output, <= 2e-5 on the fp32 output;
+  * embeddings: ||e_gpu - e_ref|| / ||e_ref|| <= 1e-3 (fp16 operands, fp32 accumulate);
+  * kNN given identical embeddings: identical ids wherever the fp64 margin exceeds 1e-6
+    (fp32 summation-order noise), distances within 2e-6.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_crops(rng, n, hmax=64, wlo=10, whi=48):
+    return [rng.integers(0, 256, (hmax, int(rng.integers(wlo, whi + 1)), 3), dtype=np.uint8) for _ in range(n)]
+
+
+@pytest.mark.parametrize("layout", ["nchw_f32", "nchw_f16", "patch_f16"])
+def test_crop_resize_matches_oracle(layout):
+    from effocr_b200 import ops
+    from oracle import transform as T
+    rng = np.random.default_rng(0)
+    shapes = [(64, 23), (64, 64), (64, 100), (30, 64), (224, 50), (300, 40), (1, 1), (2, 7), (64, 10), (48, 225), (64, 400)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in shapes]
+    pixels, images, _ = ops.pack_images(imgs)
+    boxes = [(i, 0, 0, imgs[i].shape[1], imgs[i].shape[0]) for i in range(len(imgs))]
+    # sub-rectangles, numpy-slice semantics (negative start wraps, stop clamps) and an empty slice
+    boxes += [(2, 10, 0, 60, 64), (2, -30, 0, 1000, 64), (1, 5, 3, 5, 64), (10, 100, 0, 164, 64)]
+    bt, n = ops.pack_boxes(boxes)
+    code = {"nchw_f32": ops.CROP_NCHW_F32, "nchw_f16": ops.CROP_NCHW_F16, "patch_f16": ops.CROP_PATCH_F16}[layout]
+    out = ops.crop_resize(pixels, images, bt, n, code).float().cpu().numpy()
+    if layout == "patch_f16":  # [n*196, 768] -> [n,3,224,224]
+        out = out.reshape(n, 14, 14, 3, 16, 16).transpose(0, 3, 1, 4, 2, 5).reshape(n, 3, 224, 224)
+    tol = 2e-5 if layout == "nchw_f32" else 2e-3  # fp16 ulp at |x| ~ 2.6 is 2e-3 / 2
+    for j, (i, x0, y0, x1, y1) in enumerate(boxes):
+        crop = imgs[i][y0:y1, x0:x1, :]
+        if crop.size == 0:
+            assert np.all(out[j] == 0)
+            continue
+        ref = T.paired_transform(crop)
+        assert np.abs(out[j] - ref).max() <= tol, (j, boxes[j])
+
+
+@pytest.mark.parametrize("name,batch", [("vit_tiny_patch16_224", 5), ("vit_small_patch16_224", 3)])
+def test_vit_embeddings_match_oracle(name, batch):
+    from effocr_b200.engine import VitEngine
+    from oracle import vit as V
+    sd = V.randomize_affine(V.init_vit_state_dict(name, seed=0))
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = V.vit_forward(sd, x)
+    eng = VitEngine(sd, max_batch=2)  # forces chunking (2 + 2 + 1)
+    out = eng.forward(x.cuda()).cpu()
+    rel = ((out - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    assert rel <= 1e-3, rel
+
+
+def test_vit_patch_input_equals_nchw_input():
+    from effocr_b200.engine import VitEngine
+    from oracle import vit as V
+    sd = V.init_vit_state_dict("vit_tiny_patch16_224", seed=3)
+    eng = VitEngine(sd, max_batch=4)
+    x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(2)).half().float()
+    e0 = eng.forward(x.cuda())
+    patches = x.reshape(4, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(4 * 196, 768).half().cuda()
+    e1 = eng.forward(patches)
+    assert torch.equal(e0, e1)  # same kernels, same operands: bit-identical, batch-composition independent
+    e2 = eng.forward(x[1:2].cuda())
+    assert torch.equal(e0[1:2], e2)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(94, 192, 37, 1), (94, 192, 37, 10), (10000, 384, 1024, 10), (1000, 768, 5, 32),
+                                      (5, 384, 3, 10), (300, 100, 200, 4)])
+def test_knn_matches_oracle(n, d, nq, k):
+    from effocr_b200.engine import FlatIPIndex
+    from oracle import knn as K
+    g = torch.Generator().manual_seed(n + d)
+    xb = torch.nn.functional.normalize(torch.randn(n, d, generator=g) + 2.0, dim=1)  # clustered: cos ~ 0.8
+    q = torch.nn.functional.normalize(torch.randn(nq, d, generator=g) + 2.0, dim=1)
+    index = FlatIPIndex(d)
+    index.add(xb)
+    dist, idx = index.search_device(q.cuda(), k)
+    dist, idx = dist.cpu(), idx.cpu()
+    rd, ri = K.flat_ip_search(xb, q, k)
+    s64, margin = K.margins(xb, q, k)
+    kk = min(k, n)
+    assert torch.all(idx[:, kk:] == -1)
+    decidable = margin > 1e-6
+    assert decidable.float().mean() > 0.9
+    assert torch.equal(idx[decidable][:, :kk], ri[decidable][:, :kk])
+    assert torch.allclose(dist[:, :kk], rd[:, :kk], atol=2e-6, rtol=0)
+    # undecidable rows: returned ids must still be genuine top-k up to the noise floor
+    got = torch.gather(s64, 1, idx[:, :kk])
+    best = torch.sort(s64, dim=1, descending=True).values[:, :kk]
+    assert (best - got).abs().max() < 2e-6
+
+
+def test_knn_ties_lowest_id_and_duplicates():
+    from effocr_b200.engine import FlatIPIndex
+    d = 192
+    base = torch.nn.functional.normalize(torch.randn(40, d, generator=torch.Generator().manual_seed(0)), dim=1)
+    xb = torch.cat([base, base, base[:5]], 0)  # exact duplicates: ids i, i+40 (and i+80 for i < 5)
+    index = FlatIPIndex(d)
+    index.add(xb)
+    _, idx = index.search_device(base.cuda(), 3)
+    idx = idx.cpu()
+    for i in range(40):
+        exp = [i, i + 40, i + 80] if i < 5 else [i, i + 40]
+        assert idx[i, :len(exp)].tolist() == exp
+
+
+def test_knn_remove_ids_compacts():
+    from effocr_b200.engine import FlatIPIndex
+    d = 192
+    xb = torch.nn.functional.normalize(torch.randn(50, d, generator=torch.Generator().manual_seed(1)), dim=1)
+    index = FlatIPIndex(d)
+    index.add(xb)
+    index.remove_ids(np.array([3, 10]))
+    assert index.ntotal == 48
+    _, idx = index.search_device(xb[[2, 4, 11, 49]].cuda(), 1)
+    assert idx.cpu().flatten().tolist() == [2, 3, 9, 47]

@@ -17,10 +17,14 @@ def run(M, N, K, act=0, out_f32=0, bias=True, gamma=False, resid=False, bn=0, ld
     g = torch.randn(N, device=dev) if gamma else None
     odt = torch.float32 if out_f32 else torch.float16
     R = torch.randn(M, N, device=dev).to(odt) if resid else None
-    out = torch.full((M, N), float("nan"), device=dev, dtype=odt)
+    ldo = (N + 7) // 8 * 8
+    out_full = torch.full((M, ldo), float("nan"), device=dev, dtype=odt)
+    out = out_full[:, :N]
+    if resid:
+        R_full = torch.randn(M, ldo, device=dev).to(odt); R = R_full[:, :N]
     Av = A[:, :K]
     st = lib.effocr_gemm_f16(A.data_ptr(), A.stride(0), W.data_ptr(), W.stride(0), M, N, K,
-                             _lib.ptr(b), _lib.ptr(g), _lib.ptr(R), N, out.data_ptr(), N,
+                             _lib.ptr(b), _lib.ptr(g), _lib.ptr(R), ldo, out.data_ptr(), ldo,
                              act, out_f32, bn, _lib.stream_ptr())
     _lib.check(st, "gemm")
     torch.cuda.synchronize()
