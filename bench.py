@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- EffOCR recognizer hot path on B200: char-crops/s (crop -> ViT-S/16 -> L2 norm -> kNN).
+
+Workload (BASELINE.json configs[1], the configuration the metric's target is quoted on):
+  ViT-S/16 recognizer, 224x224 crops, 10k-glyph index, batch 1024 crops per GPU, k = 10
+  (infer_effocr.py:112,317).  One "step" = one pass of the hot path over one batch of synthetic
+  u8 character crops: fused crop/resize/normalise kernel -> ViT-S encoder -> L2 normalise ->
+  exact inner-product top-10 against the index.
+
+  value : whole-job crops/s with the u8 crops already resident in HBM (CUDA events, max over ranks)
+  e2e   : the same through RecognizerPipeline.recognize_packed() with HOST (pinned) crops: H2D of the
+          crops + D2H of ids/distances inside the timed region
+  roofline     : dominant kernel, timed live with CUDA events around every launch of a profiled pass
+  cpu_baseline : the CPU oracle (torch fp32 restatement of the reference path) on a bounded sample
+
+`--impl reference` times the reference's CPU path (oracle port: reference transform restatement +
+timm-ViT restatement + fp32 IndexFlatIP restatement; faiss/timm are not installable here) with all
+host threads, each step a bounded sample of the same workload.
+
+Launch: `python bench.py --gpus 1`, or under torchrun for N > 1 (one rank per GPU, weak scaling:
+every rank processes its own batch; the glyph index is broadcast from rank 0 over NCCL at start-up,
+no steady-state collectives).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+MODEL = "vit_small_patch16_224"
+VIT_S_FLOPS_PER_CROP = 9_196_996_608  # SURVEY.md section 8d (matmul/conv FLOPs only)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="crops per GPU per step")
+    ap.add_argument("--index", type=int, default=10000, help="glyphs in the prototype index")
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def encoder_state(seed: int = 0):
+    """timm-style random init of ViT-S (no network for checkpoints); same on every rank."""
+    from effocr_b200.encoders import TimmViTParams
+
+    torch.manual_seed(seed)
+    net = TimmViTParams(MODEL)
+    return {"net." + k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, device_index: int, period_s: float = 0.1):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self._active = threading.Event()
+        self.period = period_s
+        self.h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.h = None
+
+    def run(self):
+        if self.h is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10}
+        while not self._stop_evt.is_set():
+            if self._active.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(self.period)
+
+    def begin(self):
+        self._active.set()
+
+    def end(self):
+        self._active.clear()
+
+    def stop(self):
+        self._stop_evt.set()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------- CPU baseline (oracle)
+def cpu_reference_path(sd, crops, index_vectors, k):
+    """The reference's CPU path restated: per-crop transform -> encoder -> normalize -> IndexFlatIP."""
+    from oracle import knn as OK, transform as OT, vit as OV
+
+    x = torch.from_numpy(np.stack([OT.paired_transform(c) for c in crops]))
+    with torch.no_grad():
+        emb = OV.l2_normalize(OV.vit_forward(sd, x))
+    dist, idx = OK.flat_ip_search(index_vectors, emb, k)
+    return emb, dist, idx
+
+
+def time_cpu_baseline(sd, crops, index_vectors, k, budget_s):
+    torch.set_num_threads(os.cpu_count() or 1)
+    probe = min(16, len(crops))
+    t0 = time.perf_counter()
+    cpu_reference_path(sd, crops[:probe], index_vectors, k)
+    t_probe = time.perf_counter() - t0
+    n = int(min(len(crops), max(probe, probe * budget_s / max(t_probe, 1e-3))))
+    n = max(16, n // 16 * 16)
+    t0 = time.perf_counter()
+    emb, dist, idx = cpu_reference_path(sd, crops[:n], index_vectors, k)
+    dt = time.perf_counter() - t0
+    return n, dt, emb, dist, idx
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; CPU oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from effocr_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = encoder_state(0)
+    sample = 64
+    crops, _ = synth.synthetic_crops(sample, seed=0)
+    g = torch.Generator().manual_seed(1)
+    index_vectors = torch.nn.functional.normalize(torch.randn(args.index, 384, generator=g), dim=1)
+    for _ in range(args.warmup):
+        cpu_reference_path(sd, crops[:16], index_vectors, args.k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_path(sd, crops, index_vectors, args.k)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)", "value": val,
+        "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"ViT-S/16 recognizer, 224x224 crops, {args.index}-glyph index, k={args.k}; "
+                               f"bounded sample of {sample} crops per step on the host CPU"},
+        "cpu_baseline": {"value": val, "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} crops/step x {args.steps} steps, oracle port (timm/faiss/onnxruntime not installable)"},
+        "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------- B200 arm
+def kernel_work(tag: str, B: int, D: int, mlp: int, n_index: int):
+    """Algorithmic work per LAUNCH of each kernel class at batch B."""
+    T, M = 197, B * 197
+    flops = {
+        "gemm_patch_embed": 2.0 * B * 196 * 768 * D,
+        "gemm_qkv": 2.0 * M * 3 * D * D,
+        "gemm_proj": 2.0 * M * D * D,
+        "gemm_fc1_gelu": 2.0 * M * mlp * D,
+        "gemm_fc2": 2.0 * M * mlp * D,
+        "attention": 4.0 * B * (D // 64) * T * T * 64,
+        "knn_gemm_topk": 2.0 * B * n_index * D * 3,  # three fp16 partial products per fp32 product
+    }
+    bytes_ = {
+        "layernorm": M * D * (4 + 2),
+        "crop_resize": B * (64 * 29 * 3 + 3 * 224 * 224 * 2),
+        "final_layernorm": B * D * 8,
+        "l2_normalize": B * D * 8,
+    }
+    if tag in flops:
+        return "tensor", flops[tag]
+    if tag in bytes_:
+        return "hbm", float(bytes_[tag])
+    return None, 0.0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the effocr_b200 hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from effocr_b200 import _lib, ops, synth
+    from effocr_b200.pipeline import PackedCrops, RecognizerPipeline
+
+    lib = _lib.load()
+    _lib.require_device()
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+
+    B, K = args.batch, args.k
+    sd = encoder_state(0)
+    D, mlp = 384, 1536
+    crops, _labels = synth.synthetic_crops(B, seed=rank)
+
+    # glyph index: rank 0 renders the glyphs and embeds them with the same kernels, then broadcasts
+    # the fp32 prototypes to every rank over NCCL (the only collective on the path; start-up only)
+    from effocr_b200.engine import VitEngine
+
+    boot = RecognizerPipeline(sd, torch.zeros(1, D), max_batch=B)
+    index_vectors = torch.empty((args.index, D), device="cuda", dtype=torch.float32)
+    if rank == 0:
+        glyphs = synth.glyph_images(args.index)
+        for i0 in range(0, args.index, B):
+            chunk = PackedCrops(glyphs[i0:i0 + B])
+            px, im, bx, n = chunk.to_device()
+            index_vectors[i0:i0 + n] = boot.embed_boxes(px, im, bx, n)
+        torch.cuda.synchronize()
+    if dist is not None:
+        dist.broadcast(index_vectors, src=0)
+    pipe = RecognizerPipeline.__new__(RecognizerPipeline)
+    pipe.encoder, pipe.max_batch, pipe.candidate_chars = boot.encoder, B, None
+    from effocr_b200.engine import FlatIPIndex
+
+    pipe.index = FlatIPIndex(D)
+    pipe.index.add(index_vectors.cpu())
+
+    packed = PackedCrops(crops)
+    d_pixels, d_images, d_boxes, n = packed.to_device()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return pipe.recognize_device(d_pixels, d_images, d_boxes, n, K)
+
+    def step_e2e():
+        return pipe.recognize_packed(packed, K)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    launches0 = lib.effocr_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.begin()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    barrier()
+    sampler.end()
+    ms_dev = e0.elapsed_time(e1)
+    launches = lib.effocr_launch_count() - launches0
+
+    # ---- end-to-end timing (host buffers in, host results out)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    barrier()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(e0.elapsed_time(e1), 0.0)
+    ms_e2e = max(ms_e2e, wall_e2e) if abs(wall_e2e - ms_e2e) / max(ms_e2e, 1e-6) > 0.25 else ms_e2e
+    d2h = int(res[0].nbytes + res[1].nbytes)
+
+    # ---- profiled pass: CUDA events around every launch (separate from the timed region)
+    lib.effocr_profile_reset()
+    lib.effocr_profile_enable(1)
+    prof_steps = 3
+    for _ in range(prof_steps):
+        step_device()
+    torch.cuda.synchronize()
+    import ctypes as C
+
+    prof = {}
+    for t in range(lib.effocr_profile_num_tags()):
+        cnt, tot = C.c_longlong(0), C.c_double(0.0)
+        lib.effocr_profile_read(t, C.byref(cnt), C.byref(tot))
+        if cnt.value:
+            prof[lib.effocr_profile_tag_name(t).decode()] = (cnt.value, tot.value)
+    lib.effocr_profile_enable(0)
+    sampler.stop()
+
+    # max over ranks
+    if dist is not None:
+        tt = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    total_crops = B * world * args.steps
+    value = total_crops / (ms_dev / 1e3)
+    e2e_value = total_crops / (ms_e2e / 1e3)
+
+    if rank == 0:
+        # roofline of the dominant kernel class
+        step_ms = sum(v[1] for v in prof.values()) / prof_steps
+        dom = max(prof.items(), key=lambda kv: kv[1][1])
+        dom_tag, (dom_cnt, dom_ms) = dom
+        bound, work = kernel_work(dom_tag, B, D, mlp, args.index)
+        avg_ms = dom_ms / dom_cnt
+        traffic = None
+        try:
+            traffic = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(dom_tag)
+        except Exception:
+            pass
+        if bound == "tensor":
+            peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+            achieved = work / (avg_ms / 1e3) / 1e12
+            unit = "TFLOP/s"
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+        else:
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            achieved = work / (avg_ms / 1e3) / 1e9
+            unit = "GB/s"
+            peak_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        roofline = {"kernel": dom_tag, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                    "avg_launch_ms": avg_ms, "launches_per_step": dom_cnt / prof_steps,
+                    "share_of_step": dom_ms / prof_steps / step_ms if step_ms else None}
+        kernels = {}
+        for tag, (cnt, tot) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+            b, w = kernel_work(tag, B, D, mlp, args.index)
+            ent = {"launches_per_step": cnt / prof_steps, "ms_per_step": tot / prof_steps,
+                   "share": tot / prof_steps / step_ms if step_ms else None}
+            if b == "tensor":
+                ent["tflops"] = w / (tot / cnt / 1e3) / 1e12
+            elif b == "hbm":
+                ent["gbs"] = w / (tot / cnt / 1e3) / 1e9
+            kernels[tag] = ent
+
+        cpu_block = None
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            iv = index_vectors.cpu()
+            ncpu, dt, emb_ref, _dref, idx_ref = time_cpu_baseline(sd, crops, iv, K, args.cpu_seconds)
+            # parity of the GPU path against the oracle on that sample (margin-aware)
+            emb_gpu = out[2][:ncpu].cpu()
+            idx_gpu = out[1][:ncpu].cpu()
+            rel = ((emb_gpu - emb_ref).norm(dim=1) / emb_ref.norm(dim=1)).max().item()
+            s64 = emb_ref.double() @ iv.double().t()
+            top2 = torch.topk(s64, 2, dim=1).values
+            margin = top2[:, 0] - top2[:, 1]
+            decidable = margin > 4 * rel * 1.0
+            agree = (idx_gpu[:, 0] == idx_ref[:, 0])
+            cpu_block = {"value": ncpu / dt, "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": f"first {ncpu} crops of the same batch, torch fp32 on {cores} host threads, "
+                                   "oracle port (timm/faiss/onnxruntime are not installable here)",
+                         "parity": {"max_rel_embedding_err": rel, "top1_agree": float(agree.float().mean()),
+                                    "decidable_frac": float(decidable.float().mean()),
+                                    "top1_agree_decidable": float(agree[decidable].float().mean()) if decidable.any() else None}}
+
+        line = {
+            "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)",
+            "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate", "data": "synthetic (Pillow-rendered glyph crops, random-init ViT-S)",
+            "config": {"workload": f"ViT-S/16 recognizer, 224x224 crops, {args.index}-glyph index, batch {B} crops per GPU, k={K}",
+                       "l2": "per-step activations (1.7 GB) exceed the 126 MB L2; weights (43 MB fp16) stay L2-resident by design",
+                       "parallelism": f"dp{world} over crops, index broadcast at start-up"},
+            "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": packed.h2d_bytes, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "tensor_frac_whole_step": (VIT_S_FLOPS_PER_CROP * B / (ms_dev / args.steps / 1e3) / 1e12) / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+            "kernels": kernels,
+        }
+        if cpu_block is not None:
+            line["cpu_baseline"] = cpu_block
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -33,10 +33,16 @@ SIGNATURES = {
     "effocr_abi_version": (c_int, []),
     "effocr_last_error": (C.c_char_p, []),
     "effocr_device_ok": (c_int, []),
+    "effocr_launch_count": (c_ll, []),
+    "effocr_profile_enable": (None, [c_int]),
+    "effocr_profile_reset": (None, []),
+    "effocr_profile_num_tags": (c_int, []),
+    "effocr_profile_tag_name": (C.c_char_p, [c_int]),
+    "effocr_profile_read": (c_int, [c_int, c_void_p, c_void_p]),
     "effocr_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "effocr_vit_destroy": (None, [c_void_p]),
     "effocr_vit_embed_dim": (c_int, [c_void_p]),
     "effocr_vit_max_batch": (c_int, [c_void_p]),

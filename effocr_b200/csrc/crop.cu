@@ -146,6 +146,7 @@ extern "C" int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
   if (n_boxes > 65535) return fail(EFFOCR_ERR_INVALID, "crop_resize: at most 65535 boxes per call");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(28, n_boxes);
+  KernelScope ks(PROF_CROP, s);
   switch (layout) {
     case EFFOCR_CROP_NCHW_F16: crop_resize_kernel<0><<<grid, 224, 0, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
     case EFFOCR_CROP_NCHW_F32: crop_resize_kernel<1><<<grid, 224, 0, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;

@@ -35,7 +35,10 @@ static int launch(const GemmArgs& a, const typename Epi::Params& ep, cudaStream_
   }
   const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a.M, a.N, a.K, ep);
+  {
+    KernelScope ks(a.prof_tag, stream);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, a.M, a.N, a.K, ep);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
 }

@@ -23,6 +23,7 @@ struct GemmArgs {
   const float* pos = nullptr;
   int patches = 0;
   int block_n = 0;  // 0 = choose
+  int prof_tag = PROF_GEMM_OTHER;
 };
 
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);

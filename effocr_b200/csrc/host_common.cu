@@ -1,6 +1,8 @@
 #include "host_common.h"
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "../../include/effocr_b200.h"
 
@@ -74,7 +76,78 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return EFFOCR_OK;
 }
 
+// ------------------------------------------------------------------ launch accounting / profiling
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRecord { int tag; cudaEvent_t start, stop; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof_records;   // in flight (not yet read)
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static double g_prof_ms[PROF_NUM_TAGS] = {0};
+static long long g_prof_n[PROF_NUM_TAGS] = {0};
+
+KernelScope::KernelScope(int tag, cudaStream_t stream) : slot_(-1), stream_(stream) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRecord r;
+  r.tag = tag;
+  if (!g_prof_pool.empty()) {
+    r.start = g_prof_pool.back().first; r.stop = g_prof_pool.back().second; g_prof_pool.pop_back();
+  } else {
+    if (cudaEventCreate(&r.start) != cudaSuccess || cudaEventCreate(&r.stop) != cudaSuccess) return;
+  }
+  cudaEventRecord(r.start, stream_);
+  slot_ = static_cast<int>(g_prof_records.size());
+  g_prof_records.push_back(r);
+}
+KernelScope::~KernelScope() {
+  if (slot_ < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot_ < static_cast<int>(g_prof_records.size())) cudaEventRecord(g_prof_records[slot_].stop, stream_);
+}
+
+static void prof_drain() {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof_records) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess && r.tag >= 0 && r.tag < PROF_NUM_TAGS) {
+      g_prof_ms[r.tag] += ms;
+      g_prof_n[r.tag] += 1;
+    }
+    g_prof_pool.emplace_back(r.start, r.stop);
+  }
+  g_prof_records.clear();
+}
+
+static const char* kProfNames[PROF_NUM_TAGS] = {
+    "crop_resize", "im2patch", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
+    "gemm_fc2", "final_layernorm", "l2_normalize", "knn_split", "knn_gemm_topk", "knn_merge_rerank", "misc",
+    "gemm_other", "conv_im2col", "yolo_misc", "nms", "dwconv_ln"};
+
 }  // namespace effocr
+
+extern "C" long long effocr_launch_count(void) { return effocr::g_launches.load(); }
+extern "C" void effocr_profile_enable(int on) {
+  effocr::prof_drain();
+  effocr::g_prof_on.store(on ? 1 : 0);
+}
+extern "C" void effocr_profile_reset(void) {
+  effocr::prof_drain();
+  for (int i = 0; i < effocr::PROF_NUM_TAGS; ++i) { effocr::g_prof_ms[i] = 0; effocr::g_prof_n[i] = 0; }
+}
+extern "C" int effocr_profile_num_tags(void) { return effocr::PROF_NUM_TAGS; }
+extern "C" const char* effocr_profile_tag_name(int tag) {
+  return (tag >= 0 && tag < effocr::PROF_NUM_TAGS) ? effocr::kProfNames[tag] : "";
+}
+extern "C" int effocr_profile_read(int tag, long long* launches, double* total_ms) {
+  if (tag < 0 || tag >= effocr::PROF_NUM_TAGS) return EFFOCR_ERR_INVALID;
+  effocr::prof_drain();
+  if (launches) *launches = effocr::g_prof_n[tag];
+  if (total_ms) *total_ms = effocr::g_prof_ms[tag];
+  return EFFOCR_OK;
+}
 
 extern "C" const char* effocr_last_error(void) { return effocr::g_last_error.c_str(); }
 extern "C" int effocr_abi_version(void) { return EFFOCR_B200_ABI_VERSION; }

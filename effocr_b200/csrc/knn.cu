@@ -346,7 +346,10 @@ extern "C" int effocr_knn_search(effocr_knn_t handle, const float* d_queries, in
   if (!d_queries || !d_dist || !d_idx) return fail(EFFOCR_ERR_INVALID, "knn_search: null buffer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const long long nout = static_cast<long long>(nq) * k;
-  knn_fill_kernel<<<static_cast<int>((nout + 255) / 256), 256, 0, s>>>(d_dist, d_idx, nout);
+  {
+    KernelScope ks(PROF_MISC, s);
+    knn_fill_kernel<<<static_cast<int>((nout + 255) / 256), 256, 0, s>>>(d_dist, d_idx, nout);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   if (h->N == 0) return EFFOCR_OK;
 
@@ -371,7 +374,10 @@ extern "C" int effocr_knn_search(effocr_knn_t handle, const float* d_queries, in
     EFFOCR_CUDA(cudaMalloc(&h->part_idx, need_p * 4));
     h->part_cap = need_p;
   }
-  knn_split_kernel<<<148 * 4, 256, 0, s>>>(d_queries, h->qsplit, nq, nq_pad, h->D, h->Dp, 0);
+  {
+    KernelScope ks(PROF_KNN_SPLIT, s);
+    knn_split_kernel<<<148 * 4, 256, 0, s>>>(d_queries, h->qsplit, nq, nq_pad, h->D, h->Dp, 0);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   CUtensorMap tq, tx;
   EFFOCR_TRY(make_tmap_f16_2d(&tq, h->qsplit, nq_pad, 3 * h->Dp, 3 * h->Dp, kKnnBM));
@@ -381,11 +387,17 @@ extern "C" int effocr_knn_search(effocr_knn_t handle, const float* d_queries, in
     EFFOCR_CUDA(cudaFuncSetAttribute(knn_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes));
     attr = true;
   }
-  knn_gemm_topk_kernel<<<m_tiles * splits, kKnnThreads, kKnnSmemBytes, s>>>(tq, tx, nq, h->N, h->Dp, n_tiles, splits,
-                                                                          h->part_val, h->part_idx);
+  {
+    KernelScope ks(PROF_KNN_GEMM, s);
+    knn_gemm_topk_kernel<<<m_tiles * splits, kKnnThreads, kKnnSmemBytes, s>>>(tq, tx, nq, h->N, h->Dp, n_tiles, splits,
+                                                                            h->part_val, h->part_idx);
+  }
   EFFOCR_CUDA(cudaGetLastError());
-  knn_merge_rerank_kernel<<<(nq + 3) / 4, 128, 0, s>>>(h->part_val, h->part_idx, splits * 2, d_queries, h->xb, nq, h->D,
-                                                       k, d_dist, d_idx);
+  {
+    KernelScope ks(PROF_KNN_MERGE, s);
+    knn_merge_rerank_kernel<<<(nq + 3) / 4, 128, 0, s>>>(h->part_val, h->part_idx, splits * 2, d_queries, h->xb, nq,
+                                                         h->D, k, d_dist, d_idx);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
 }
@@ -393,7 +405,10 @@ extern "C" int effocr_knn_search(effocr_knn_t handle, const float* d_queries, in
 extern "C" int effocr_l2_normalize(const float* d_x, float* d_out, int rows, int dim, float eps, void* stream) {
   EFFOCR_TRY(require_sm100());
   if (rows <= 0) return EFFOCR_OK;
-  l2_normalize_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_out, rows, dim, eps);
+  {
+    KernelScope ks(PROF_L2NORM, reinterpret_cast<cudaStream_t>(stream));
+    l2_normalize_kernel<<<(rows + 7) / 8, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_x, d_out, rows, dim, eps);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
 }

@@ -20,6 +20,7 @@ struct VitLayer {
 
 struct VitHandle {
   int D = 0, H = 0, depth = 0, mlp = 0, max_batch = 0;
+  float eps = 1e-6f;
   static constexpr int T = 197, P = 196, PK = 768;
   __half* w_patch = nullptr;
   float *b_patch = nullptr, *cls = nullptr, *pos = nullptr, *lnf_w = nullptr, *lnf_b = nullptr;
@@ -57,9 +58,10 @@ struct VitHandle {
 
 template <typename OutT>
 static int layernorm_launch(const float* x, long long ldx, const float* g, const float* b, OutT* out, long long ldo,
-                            int rows, int D, float eps, cudaStream_t s) {
+                            int rows, int D, float eps, cudaStream_t s, int tag) {
   const int wpb = 8;
   const int grid = (rows + wpb - 1) / wpb;
+  KernelScope ks(tag, s);
   switch (D) {
     case 96: layernorm_rows_kernel<96, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
     case 192: layernorm_rows_kernel<192, OutT><<<grid, wpb * 32, 0, s>>>(x, ldx, g, b, out, ldo, rows, eps); break;
@@ -72,12 +74,12 @@ static int layernorm_launch(const float* x, long long ldx, const float* g, const
 }
 
 int layernorm_f16(const float* x, long long ldx, const float* g, const float* b, __half* out, long long ldo, int rows,
-                  int D, float eps, cudaStream_t s) {
-  return layernorm_launch<__half>(x, ldx, g, b, out, ldo, rows, D, eps, s);
+                  int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM) {
+  return layernorm_launch<__half>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 int layernorm_f32(const float* x, long long ldx, const float* g, const float* b, float* out, long long ldo, int rows,
-                  int D, float eps, cudaStream_t s) {
-  return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s);
+                  int D, float eps, cudaStream_t s, int tag = PROF_FINAL_LN) {
+  return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s) {
@@ -88,7 +90,10 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     attr = true;
   }
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  attention_197x64_kernel<<<batch * H, kAttnThreads, kAttnSmemBytes, s>>>(qkv, out, T, H, scale_log2e);
+  {
+    KernelScope ks(PROF_ATTENTION, s);
+    attention_197x64_kernel<<<batch * H, kAttnThreads, kAttnSmemBytes, s>>>(qkv, out, T, H, scale_log2e);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
 }
@@ -102,33 +107,37 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
   g.A = v->patches; g.lda = VitHandle::PK; g.W = v->w_patch; g.ldw = VitHandle::PK;
   g.M = B * VitHandle::P; g.N = D; g.K = VitHandle::PK;
   g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = v->b_patch; g.pos = v->pos; g.patches = VitHandle::P;
+  g.prof_tag = PROF_GEMM_PATCH;
   EFFOCR_TRY(gemm_f16(g, s));
-  cls_pos_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(v->x, v->cls, v->pos, B, T, D);
+  {
+    KernelScope ks(PROF_MISC, s);
+    cls_pos_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(v->x, v->cls, v->pos, B, T, D);
+  }
   EFFOCR_CUDA(cudaGetLastError());
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
-    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, 1e-6f, s));
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s));
     g = GemmArgs();
     g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
-    g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv;
+    g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
     EFFOCR_TRY(gemm_f16(g, s));
     EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
     g = GemmArgs();
     g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
-    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D;
+    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
     EFFOCR_TRY(gemm_f16(g, s));
-    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, 1e-6f, s));
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s));
     g = GemmArgs();
     g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = M; g.N = v->mlp; g.K = D;
-    g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1;
+    g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1; g.prof_tag = PROF_GEMM_FC1;
     EFFOCR_TRY(gemm_f16(g, s));
     g = GemmArgs();
     g.A = v->mid; g.lda = v->mlp; g.W = L.w_fc2; g.ldw = v->mlp; g.M = M; g.N = D; g.K = v->mlp;
-    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_fc2; g.resid = v->x; g.ldr = D;
+    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_fc2; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_FC2;
     EFFOCR_TRY(gemm_f16(g, s));
   }
   // final LayerNorm on the CLS rows only (row stride T * D)
-  EFFOCR_TRY(layernorm_f32(v->x, static_cast<long long>(T) * D, v->lnf_w, v->lnf_b, emb, D, B, D, 1e-6f, s));
+  EFFOCR_TRY(layernorm_f32(v->x, static_cast<long long>(T) * D, v->lnf_w, v->lnf_b, emb, D, B, D, v->eps, s));
   return EFFOCR_OK;
 }
 
@@ -136,7 +145,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
 
 using namespace effocr;
 
-extern "C" int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch,
+extern "C" int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch, float ln_eps,
                                  const float* const* h_weights, int n_weights, effocr_vit_t* out) {
   if (!out) return fail(EFFOCR_ERR_INVALID, "vit_create: null out");
   *out = nullptr;
@@ -147,7 +156,7 @@ extern "C" int effocr_vit_create(int embed_dim, int num_heads, int depth, int ml
   if (n_weights != 4 + 12 * depth + 2) return fail(EFFOCR_ERR_INVALID, "vit_create: expected 4 + 12*depth + 2 weight tensors");
   if (max_batch <= 0 || mlp_dim % 8 != 0) return fail(EFFOCR_ERR_INVALID, "vit_create: bad max_batch / mlp_dim");
   VitHandle* v = new VitHandle();
-  v->D = embed_dim; v->H = num_heads; v->depth = depth; v->mlp = mlp_dim; v->max_batch = max_batch;
+  v->D = embed_dim; v->H = num_heads; v->depth = depth; v->mlp = mlp_dim; v->max_batch = max_batch; v->eps = ln_eps;
   const int D = embed_dim;
   int st = EFFOCR_OK;
   auto W = [&](int i) { return h_weights[i]; };
@@ -214,7 +223,10 @@ extern "C" int effocr_vit_forward(effocr_vit_t h, const void* d_input, int input
       const float* img = reinterpret_cast<const float*>(d_input) + size_t(b0) * 3 * 224 * 224;
       const long long total = static_cast<long long>(B) * 196 * 96;
       const int grid = static_cast<int>((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-      im2patch_kernel<<<grid, 256, 0, s>>>(img, v->patches, B);
+      {
+        KernelScope ks(PROF_IM2PATCH, s);
+        im2patch_kernel<<<grid, 256, 0, s>>>(img, v->patches, B);
+      }
       EFFOCR_CUDA(cudaGetLastError());
     } else if (input_kind == EFFOCR_INPUT_PATCH_F16) {
       const __half* p = reinterpret_cast<const __half*>(d_input) + size_t(b0) * 196 * 768;

@@ -34,7 +34,7 @@ def vit_weight_order(depth: int):
 class VitEngine:
     """Device-resident ViT encoder (fp16 weights, fp32 residual stream) behind effocr_vit_*."""
 
-    def __init__(self, state_dict, prefix: str = "net.", max_batch: int = 1024, device=None):
+    def __init__(self, state_dict, prefix: str = "net.", max_batch: int = 1024, device=None, ln_eps: float = 1e-6):
         self._lib = _lib.load()
         if device is not None:
             torch.cuda.set_device(device)
@@ -57,7 +57,7 @@ class VitEngine:
             ptrs[i] = a.ctypes.data
         h = C.c_void_p()
         _lib.check(self._lib.effocr_vit_create(self.embed_dim, self.num_heads, self.depth, self.mlp_dim, self.max_batch,
-                                               ptrs, len(ptrs), C.byref(h)), "effocr_vit_create")
+                                               float(ln_eps), ptrs, len(ptrs), C.byref(h)), "effocr_vit_create")
         self._h = h
         self._lock = threading.Lock()  # one workspace per handle: serialise concurrent run() callers
         self.device = torch.device("cuda", torch.cuda.current_device())

@@ -1,0 +1,100 @@
+"""Device-resident recognizer pipeline: boxes -> fused crop -> ViT -> L2 norm -> exact kNN.
+
+This is the B200-first replacement for the per-line loop of /root/reference/infer_effocr.py:280-338
+and phases 2-3 of infer_effocr_onnx_multi.py:307-386: all crops of all lines go through ONE crop
+launch that writes the encoder's patch buffer in place, embeddings and scores never leave the
+device, and only the k ids (and distances) per character come back to the host.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .engine import FlatIPIndex, VitEngine
+
+
+class PackedCrops:
+    """Pinned host staging for one batch: pixels + image descriptors + crop boxes."""
+
+    def __init__(self, arrays, boxes=None):
+        descs = np.zeros(len(arrays), dtype=ops.IMAGE_DESC_DTYPE)
+        off = 0
+        for i, a in enumerate(arrays):
+            h, w, _ = a.shape
+            descs[i] = (off, h, w, w * 3, 0)
+            off += (h * w * 3 + 255) // 256 * 256
+        pin = torch.cuda.is_available()
+        self.pixels = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=pin)
+        hv = self.pixels.numpy()
+        for i, a in enumerate(arrays):
+            o = int(descs[i]["offset"])
+            hv[o:o + a.size] = np.ascontiguousarray(a).reshape(-1)
+        if boxes is None:
+            boxes = [(i, 0, 0, a.shape[1], a.shape[0]) for i, a in enumerate(arrays)]
+        arr = np.asarray(list(boxes), dtype=np.int32).reshape(-1, 5)
+        rec = np.zeros(len(arr), dtype=ops.CROP_BOX_DTYPE)
+        for k, name in enumerate(("image", "x0", "y0", "x1", "y1")):
+            rec[name] = arr[:, k]
+        self.images = torch.from_numpy(descs.view(np.uint8).copy())
+        self.boxes = torch.from_numpy(rec.view(np.uint8).copy())
+        if pin:
+            self.images = self.images.pin_memory()
+            self.boxes = self.boxes.pin_memory()
+        self.n = len(arr)
+
+    @property
+    def h2d_bytes(self) -> int:
+        return self.pixels.numel() + self.images.numel() + self.boxes.numel()
+
+    def to_device(self):
+        return (self.pixels.cuda(non_blocking=True), self.images.cuda(non_blocking=True),
+                self.boxes.cuda(non_blocking=True), self.n)
+
+
+class RecognizerPipeline:
+
+    def __init__(self, encoder_state, index, candidate_chars=None, max_batch: int = 1024, prefix: str | None = None):
+        if prefix is None:
+            prefix = "net." if any(k.startswith("net.") for k in encoder_state) else ""
+        self.encoder = VitEngine(encoder_state, prefix=prefix, max_batch=max_batch)
+        if not isinstance(index, FlatIPIndex):
+            vec = torch.as_tensor(index, dtype=torch.float32)
+            index = FlatIPIndex(vec.shape[1])
+            index.add(vec)
+        self.index = index
+        self.candidate_chars = candidate_chars
+        self.max_batch = max_batch
+
+    # ---- device-resident stage-wise API
+    def embed_boxes(self, pixels, images, boxes, n: int) -> torch.Tensor:
+        """-> L2-normalised embeddings, CUDA f32 [n, D]."""
+        out = torch.empty((n, self.encoder.embed_dim), device=pixels.device, dtype=torch.float32)
+        itemsize = ops.CROP_BOX_DTYPE.itemsize
+        for b0 in range(0, n, self.max_batch):
+            b = min(self.max_batch, n - b0)
+            ops.crop_resize(pixels, images, boxes[b0 * itemsize:], b, ops.CROP_PATCH_F16, out=self.encoder.patch_buffer(b))
+            self.encoder.forward(None, batch=b, out=out[b0:b0 + b])
+        return ops.l2_normalize(out)
+
+    def recognize_device(self, pixels, images, boxes, n: int, k: int = 10):
+        emb = self.embed_boxes(pixels, images, boxes, n)
+        dist, idx = self.index.search_device(emb, k)
+        return dist, idx, emb
+
+    # ---- host-facing API (what a caller holding numpy crops uses)
+    def recognize_packed(self, packed: PackedCrops, k: int = 10):
+        pixels, images, boxes, n = packed.to_device()
+        dist, idx, _ = self.recognize_device(pixels, images, boxes, n, k)
+        return dist.cpu().numpy(), idx.cpu().numpy()
+
+    def recognize_crops(self, crops, k: int = 10):
+        """crops: list of u8 [h, w, 3] arrays -> (distances [n,k], ids [n,k]) numpy."""
+        if len(crops) == 0:
+            return np.zeros((0, k), np.float32), np.zeros((0, k), np.int64)
+        return self.recognize_packed(PackedCrops(crops), k)
+
+    def decode(self, idx: np.ndarray):
+        """ids -> nearest-neighbour strings per char and the line text (infer_effocr.py:318-338)."""
+        nearest = [[self.candidate_chars[j] for j in row if j >= 0] for row in idx.tolist()]
+        return nearest, "".join(x[0] for x in nearest).strip()

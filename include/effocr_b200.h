@@ -45,6 +45,17 @@ EFFOCR_API const char* effocr_last_error(void);
 /* 0 when the current CUDA device is an sm_100 part, EFFOCR_ERR_NO_DEVICE / _CUDA otherwise. */
 EFFOCR_API int effocr_device_ok(void);
 
+/* ---- launch accounting and per-kernel timing (what bench.py's gpu_launches / roofline report) ----
+ * effocr_launch_count: kernels this library has launched since load.  With profiling enabled every
+ * launch is bracketed by CUDA events on its own stream; effocr_profile_read synchronises the device
+ * and returns launches / summed milliseconds for one kernel class (names: effocr_profile_tag_name). */
+EFFOCR_API long long effocr_launch_count(void);
+EFFOCR_API void effocr_profile_enable(int on);
+EFFOCR_API void effocr_profile_reset(void);
+EFFOCR_API int effocr_profile_num_tags(void);
+EFFOCR_API const char* effocr_profile_tag_name(int tag);
+EFFOCR_API int effocr_profile_read(int tag, long long* launches, double* total_ms);
+
 /* ---- tcgen05 GEMM building block ----------------------------------------------------------
  * out[M,N] = act(A[M,K] . W[N,K]^T + bias) * gamma + resid      fp16 operands, fp32 accumulate.
  * Replaces the ATen/oneDNN/ORT matmul + elementwise calls inside timm Block.forward and yolov5
@@ -88,12 +99,13 @@ EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
  *              attn.proj.bias, norm2.weight, norm2.bias, mlp.fc1.weight [4D,D], mlp.fc1.bias,
  *              mlp.fc2.weight [D,4D], mlp.fc2.bias,
  *   norm.weight, norm.bias.
+ * ln_eps: LayerNorm epsilon (timm ViT: 1e-6).
  * The handle owns its weights and a workspace for max_batch crops (larger batches are chunked). */
 typedef struct effocr_vit_s* effocr_vit_t;
 #define EFFOCR_INPUT_NCHW_F32 0     /* d_input: fp32 [B,3,224,224] (the reference's tensor) */
 #define EFFOCR_INPUT_PATCH_F16 1    /* d_input: fp16 [B*196,768] patch-major */
 #define EFFOCR_INPUT_PATCH_BUFFER 2 /* input already written into effocr_vit_patch_buffer(); B <= max_batch */
-EFFOCR_API int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch,
+EFFOCR_API int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch, float ln_eps,
                                  const float* const* h_weights, int n_weights, effocr_vit_t* out);
 EFFOCR_API void effocr_vit_destroy(effocr_vit_t h);
 EFFOCR_API int effocr_vit_embed_dim(effocr_vit_t h);
