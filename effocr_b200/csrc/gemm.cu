@@ -2,6 +2,7 @@
 
 #include "../../include/effocr_b200.h"
 #include "gemm_sm100.cuh"
+#include "gemm_sm100_tma_epi.cuh"
 
 namespace effocr {
 
@@ -67,6 +68,62 @@ static int launch_store(int bn, const GemmArgs& a, cudaStream_t stream) {
   return launch_bn<Epi>(bn, a, ep, stream);
 }
 
+// ---- TMA-store / TMA-reduce epilogue path (aligned outputs, no separate residual buffer)
+template <int BN, int ACT, bool F32, bool RED>
+static int launch_tma(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmTmaCfg<BN, F32>;
+  CUtensorMap ta, tb, tc;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN));
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, kBlockM, 32, F32 ? 128 : 64));
+  auto kern = gemm_tn_tma_kernel<BN, ACT, F32, RED>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  EpiTmaParams ep;
+  ep.bias = a.bias;
+  ep.gamma = a.gamma;
+  {
+    KernelScope ks(a.prof_tag, stream);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+template <int ACT, bool F32, bool RED>
+static int launch_tma_bn(int bn, const GemmArgs& a, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_tma<64, ACT, F32, RED>(a, stream);
+    case 128: return launch_tma<128, ACT, F32, RED>(a, stream);
+    case 192: return launch_tma<192, ACT, F32, RED>(a, stream);
+    case 256: return launch_tma<256, ACT, F32, RED>(a, stream);
+  }
+  return fail(EFFOCR_ERR_INVALID, "block_n must be 64, 128, 192 or 256");
+}
+
+// Returns -1 when the TMA epilogue does not apply (caller falls back to the direct-store epilogue).
+static int try_gemm_tma(int bn, const GemmArgs& a, cudaStream_t stream) {
+  if (a.pos || a.epilogue == 1) return -1;
+  const bool inplace = a.resid != nullptr && a.resid == a.out && a.ldr == a.ldo;
+  if (a.resid && !inplace) return -1;
+  if (a.out_f32) {
+    if (a.act != ACT_NONE) return -1;
+    return inplace ? launch_tma_bn<ACT_NONE, true, true>(bn, a, stream) : launch_tma_bn<ACT_NONE, true, false>(bn, a, stream);
+  }
+  if (inplace) return -1;  // fp16 in-place residual: not needed by any model here
+  switch (a.act) {
+    case ACT_NONE: return launch_tma_bn<ACT_NONE, false, false>(bn, a, stream);
+    case ACT_GELU: return launch_tma_bn<ACT_GELU, false, false>(bn, a, stream);
+    case ACT_SILU: return launch_tma_bn<ACT_SILU, false, false>(bn, a, stream);
+  }
+  return -1;
+}
+
 int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return fail(EFFOCR_ERR_INVALID, "gemm: empty problem");
   if (!a.A || !a.W || !a.out) return fail(EFFOCR_ERR_INVALID, "gemm: null operand");
@@ -80,6 +137,10 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
   if ((a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) || (a.gamma && (reinterpret_cast<uintptr_t>(a.gamma) & 15)))
     return fail(EFFOCR_ERR_INVALID, "gemm: bias / gamma must be 16-byte aligned");
   const int bn = a.block_n ? a.block_n : choose_block_n(a.N);
+  {
+    const int st = try_gemm_tma(bn, a, stream);
+    if (st >= 0) return st;
+  }
 
   if (a.pos) {
     if (a.N % 32 != 0 || a.patches <= 0 || !a.bias || !a.out_f32)
@@ -123,6 +184,8 @@ extern "C" int effocr_gemm_f16(const void* A, long long lda, const void* W, long
   a.ldw = ldw;
   a.M = M; a.N = N; a.K = K;
   a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr;
-  a.out = out; a.ldo = ldo; a.act = act; a.out_f32 = out_f32; a.block_n = block_n;
+  a.out = out; a.ldo = ldo; a.act = act; a.out_f32 = out_f32;
+  a.block_n = block_n & 0xffff;
+  a.epilogue = (block_n >> 16) & 1;  // bit 16 forces the direct-store epilogue (tests compare both)
   return effocr::gemm_f16(a, reinterpret_cast<cudaStream_t>(stream));
 }

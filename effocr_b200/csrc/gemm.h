@@ -24,6 +24,7 @@ struct GemmArgs {
   int patches = 0;
   int block_n = 0;  // 0 = choose
   int prof_tag = PROF_GEMM_OTHER;
+  int epilogue = 0;  // 0 = TMA-store epilogue when applicable, 1 = force the direct-store epilogue
 };
 
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);

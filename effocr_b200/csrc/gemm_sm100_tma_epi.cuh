@@ -1,0 +1,248 @@
+// Second-generation epilogue for the tcgen05 GEMM (gemm_sm100.cuh holds the mainloop description):
+// accumulators go TMEM -> registers -> fused op -> swizzled shared-memory staging tile -> TMA store,
+// so every global write is a full 128-byte line issued by the TMA engine instead of 32 scattered
+// 16-byte stores per warp instruction (the first-round epilogue spent > 3000 L1 wavefront-cycles per
+// tile on those, more than the MMAs of the tile).  The fp32 residual update of the ViT stream,
+//        x <- x + (A.W^T + bias) * gamma,
+// is done by the TMA reduce-add (cp.reduce.async.bulk.tensor ... .add): the read-modify-write of x
+// happens in L2 and the SM never loads the residual.
+//
+// Each half of the tile's columns is owned by 4 epilogue warps (one per TMEM lane quarter); they
+// walk their 32-column chunks through two staging buffers, synchronising with a named barrier.
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace effocr {
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int BLOCK_N, bool OUT_F32>
+struct GemmTmaCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagingBytes = kBlockM * 32 * (OUT_F32 ? 4 : 2);  // one 128 x 32 chunk
+  static constexpr int kNumStaging = 4;                                    // 2 per column half
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kStagesRaw = (kSmemLimit - 1024 - kBarrierBytes - kNumStaging * kStagingBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kNumStaging * kStagingBytes + kBarrierBytes + 1024;
+  static constexpr int kTmemCols = GemmCfg<BLOCK_N>::kTmemCols;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+struct EpiTmaParams {
+  const float* bias;   // [N] or nullptr
+  const float* gamma;  // [N] or nullptr
+};
+
+// ACT: activation; OUT_F32: output element type; REDUCE: TMA reduce-add into the output (in-place residual)
+template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiTmaParams ep) {
+  using Cfg = GemmTmaCfg<BLOCK_N, OUT_F32>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+  uint8_t* smem_c = smem + STAGES * Cfg::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kNumStaging * Cfg::kStagingBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0) {
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * kBlockM;
+        const int n0 = (tile % num_n) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          tma_load_2d(&tma_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK, m0);
+          tma_load_2d(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int q = warp_idx & 3;            // TMEM lane quarter == 32-row band of the tile
+    const int half = (warp_idx - 4) >> 2;  // column half owned by this 4-warp group
+    constexpr int CHUNKS = BLOCK_N / 64;   // 32-column chunks per half
+    const int r = q * 32 + lane;           // row inside the tile
+    const bool issuer = (q == 0 && lane == 0);
+    const int bar_id = 1 + half;
+    uint8_t* stg[2] = {smem_c + (half * 2 + 0) * Cfg::kStagingBytes, smem_c + (half * 2 + 1) * Cfg::kStagingBytes};
+    int buf = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const int m0 = (tile / num_n) * kBlockM;
+      const int n0 = (tile % num_n) * BLOCK_N;
+      mbar_wait(&tfull_bar[as], aphase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int cc = half * CHUNKS + c;
+        const int col0 = n0 + cc * 32;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cc * 32, v);
+        tmem_ld_wait();
+        if (c == CHUNKS - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+        float y[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
+        if (col0 + 32 <= N) {
+          if (ep.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+              y[i] += b.x; y[i + 1] += b.y; y[i + 2] += b.z; y[i + 3] += b.w;
+            }
+          }
+        } else if (ep.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) y[i] += __ldg(ep.bias + col0 + i);
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (ACT == ACT_GELU) y[i] = gelu_erf(y[i]);
+          if (ACT == ACT_SILU) y[i] = silu(y[i]);
+        }
+        if (ep.gamma) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < N) y[i] *= __ldg(ep.gamma + col0 + i);
+        }
+        // staging buffer `buf` was last read by the TMA store issued two chunks ago
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(bar_id, 128);
+        uint8_t* dst = stg[buf];
+        if constexpr (OUT_F32) {
+          // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + r * 128 + ((j ^ (r & 7)) << 4)) =
+                make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        } else {
+          // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+            *reinterpret_cast<uint4*>(dst + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = pk;
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          if (REDUCE) tma_reduce_add_2d(&tma_c, dst, col0, m0);
+          else tma_store_2d(&tma_c, dst, col0, m0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (issuer) tma_store_wait_all<0>();  // global writes complete before the CTA exits
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace effocr

@@ -76,6 +76,30 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   return EFFOCR_OK;
 }
 
+int make_tmap_2d(CUtensorMap* out, const void* base, int esz, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(EFFOCR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * esz) % 16 != 0)
+    return fail(EFFOCR_ERR_INVALID, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+  if (box_rows == 0 || box_rows > 256 || box_cols == 0 || box_cols > 256) return fail(EFFOCR_ERR_INVALID, "TMA box out of range");
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (swizzle_bytes && static_cast<int>(box_cols) * esz != swizzle_bytes)
+    return fail(EFFOCR_ERR_INVALID, "TMA box width must equal the swizzle span");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * static_cast<uint64_t>(esz)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EFFOCR_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return EFFOCR_OK;
+}
+
 // ------------------------------------------------------------------ launch accounting / profiling
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};

@@ -57,4 +57,9 @@ int require_sm100();
 int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows);
 
+// General 2-D row-major tensor map: element size esz (2 = fp16, 4 = fp32), box = box_rows x box_cols,
+// swizzle_bytes in {0, 32, 64, 128} (must equal box_cols * esz when non-zero).
+int make_tmap_2d(CUtensorMap* out, const void* base, int esz, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
+
 }  // namespace effocr

@@ -30,7 +30,7 @@ def _cuda(t: torch.Tensor, dtype=None, name="tensor") -> torch.Tensor:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = ACT_NONE, out_dtype=torch.float16, resid=None,
-         gamma=None, out=None, block_n: int = 0) -> torch.Tensor:
+         gamma=None, out=None, block_n: int = 0, direct_epilogue: bool = False) -> torch.Tensor:
     """out = act(a @ w.T + bias) * gamma + resid, fp16 operands, fp32 accumulate (tcgen05)."""
     lib = _lib.load()
     a = _cuda(a, torch.float16, "a")
@@ -44,7 +44,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = ACT_NONE, out_d
     f32 = 1 if out.dtype == torch.float32 else 0
     _lib.check(lib.effocr_gemm_f16(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K, _lib.ptr(bias),
                                    _lib.ptr(gamma), _lib.ptr(resid), resid.stride(0) if resid is not None else 0,
-                                   out.data_ptr(), out.stride(0), act, f32, block_n, _lib.stream_ptr()), "effocr_gemm_f16")
+                                   out.data_ptr(), out.stride(0), act, f32, block_n | (0x10000 if direct_epilogue else 0),
+                                   _lib.stream_ptr()), "effocr_gemm_f16")
     return out
 
 

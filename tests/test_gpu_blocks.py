@@ -22,7 +22,8 @@ def _rel(a, b):
     (3000, 21, 512, 0, 1, False, False, 64),
     (20000, 1152, 384, 0, 0, False, False, 0),   # many tiles per CTA: phase wrap of both pipelines
 ])
-def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn):
+@pytest.mark.parametrize("direct", [False, True])
+def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn, direct):
     from effocr_b200 import ops
     torch.manual_seed(0)
     a = (torch.randn(M, K, device="cuda") * 0.5).half()
@@ -32,7 +33,7 @@ def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn):
     odt = torch.float32 if f32 else torch.float16
     ld = (N + 7) // 8 * 8
     r = torch.randn(M, ld, device="cuda").to(odt)[:, :N] if resid else None
-    out = ops.gemm(a, w, bias=b, act=act, out_dtype=odt, resid=r, gamma=g, block_n=bn)
+    out = ops.gemm(a, w, bias=b, act=act, out_dtype=odt, resid=r, gamma=g, block_n=bn, direct_epilogue=direct)
     ref = a.float() @ w.float().t() + b
     if act == 1:
         ref = torch.nn.functional.gelu(ref)
@@ -47,15 +48,21 @@ def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn):
     assert torch.isfinite(out.float()).all()
 
 
-def test_gemm_inplace_residual():
+@pytest.mark.parametrize("direct", [False, True])
+@pytest.mark.parametrize("M,N,K,gamma", [(2000, 384, 384, False), (5000, 384, 1536, False), (1333, 96, 384, True),
+                                          (4100, 768, 3072, True)])
+def test_gemm_inplace_residual(M, N, K, gamma, direct):
+    """x <- x + (a @ w.T + bias) * gamma: TMA reduce-add epilogue vs the direct read-modify-write one."""
     from effocr_b200 import ops
     torch.manual_seed(1)
-    M, N, K = 2000, 384, 384
     a = (torch.randn(M, K, device="cuda") * 0.5).half()
     w = (torch.randn(N, K, device="cuda") * 0.05).half()
+    b = torch.randn(N, device="cuda")
+    g = torch.randn(N, device="cuda") if gamma else None
     x = torch.randn(M, N, device="cuda")
-    ref = x + a.float() @ w.float().t()
-    ops.gemm(a, w, out_dtype=torch.float32, resid=x, out=x)
+    upd = a.float() @ w.float().t() + b
+    ref = x + (upd * g if gamma else upd)
+    ops.gemm(a, w, bias=b, gamma=g, out_dtype=torch.float32, resid=x, out=x, direct_epilogue=direct)
     assert _rel(x, ref) < 2e-6
 
 
