@@ -63,7 +63,7 @@ def test_gemm_inplace_residual(M, N, K, gamma, direct):
     upd = a.float() @ w.float().t() + b
     ref = x + (upd * g if gamma else upd)
     ops.gemm(a, w, bias=b, gamma=g, out_dtype=torch.float32, resid=x, out=x, direct_epilogue=direct)
-    assert _rel(x, ref) < 2e-6
+    assert _rel(x, ref) < (2e-6 if K <= 1536 else 5e-6)  # fp32 accumulation-order noise grows with K
 
 
 @pytest.mark.parametrize("dim", [96, 192, 384, 768])
