@@ -75,7 +75,7 @@ static int launch_tma(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap ta, tb, tc;
   EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
   EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN));
-  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, kBlockM, 32, F32 ? 128 : 64));
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, 32, 32, F32 ? 128 : 64));
   auto kern = gemm_tn_tma_kernel<BN, ACT, F32, RED>;
   static bool attr_done = false;
   if (!attr_done) {

@@ -7,8 +7,10 @@
 // is done by the TMA reduce-add (cp.reduce.async.bulk.tensor ... .add): the read-modify-write of x
 // happens in L2 and the SM never loads the residual.
 //
-// Each half of the tile's columns is owned by 4 epilogue warps (one per TMEM lane quarter); they
-// walk their 32-column chunks through two staging buffers, synchronising with a named barrier.
+// Each of the 8 epilogue warps owns a 32-row band (its TMEM lane quarter) of one column half and
+// walks its 32-column chunks through a private pair of staging buffers with private TMA stores, so
+// there is no cross-warp barrier in the epilogue; the TMEM load of chunk c+1 is in flight while
+// chunk c is being processed.
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -44,8 +46,9 @@ struct GemmTmaCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagingBytes = kBlockM * 32 * (OUT_F32 ? 4 : 2);  // one 128 x 32 chunk
-  static constexpr int kNumStaging = 4;                                    // 2 per column half
+  static constexpr int kWarpStagingBytes = 32 * 32 * (OUT_F32 ? 4 : 2);  // one warp's 32 x 32 chunk
+  static constexpr int kStagingBytes = 4 * kWarpStagingBytes;            // per 4-warp column half
+  static constexpr int kNumStaging = 4;                                  // 8 warps x 2 buffers
   static constexpr int kBarrierBytes = 512;
   static constexpr int kStagesRaw = (kSmemLimit - 1024 - kBarrierBytes - kNumStaging * kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -153,69 +156,73 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
     }
   } else if (warp_idx >= 4) {
-    const int q = warp_idx & 3;            // TMEM lane quarter == 32-row band of the tile
-    const int half = (warp_idx - 4) >> 2;  // column half owned by this 4-warp group
-    constexpr int CHUNKS = BLOCK_N / 64;   // 32-column chunks per half
-    const int r = q * 32 + lane;           // row inside the tile
-    const bool issuer = (q == 0 && lane == 0);
-    const int bar_id = 1 + half;
-    uint8_t* stg[2] = {smem_c + (half * 2 + 0) * Cfg::kStagingBytes, smem_c + (half * 2 + 1) * Cfg::kStagingBytes};
+    // Each epilogue warp owns a 32-row band (its TMEM lane quarter q) of one column half and works
+    // alone: private double-buffered staging tile, private TMA stores -- no cross-warp barriers.
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 4) >> 2;
+    constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per half
+    uint8_t* stg = smem_c + (warp_idx - 4) * 2 * Cfg::kWarpStagingBytes;
     int buf = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
-      const int m0 = (tile / num_n) * kBlockM;
-      const int n0 = (tile % num_n) * BLOCK_N;
+      const int m0 = (tile / num_n) * kBlockM + q * 32;
+      const int n0 = (tile % num_n) * BLOCK_N + half * (BLOCK_N / 2);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
-#pragma unroll 1
+      uint32_t v[2][32];
+      tmem_ld_32x32b_x32(tbase, v[0]);
+#pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
-        const int cc = half * CHUNKS + c;
-        const int col0 = n0 + cc * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cc * 32, v);
+        const int col0 = n0 + c * 32;
+        // bias for this chunk: issued before the TMEM wait so both latencies overlap
+        float bv[32];
+        const bool full = (col0 + 32 <= N);
+        if (ep.bias) {
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+              bv[i] = b.x; bv[i + 1] = b.y; bv[i + 2] = b.z; bv[i + 3] = b.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bv[i] = (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
+          }
+        }
         tmem_ld_wait();
-        if (c == CHUNKS - 1) {  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          tcgen05_fence_before();
+        if (c + 1 < CHUNKS) {
+          tmem_ld_32x32b_x32(tbase + (c + 1) * 32, v[(c + 1) & 1]);  // prefetch the next chunk
+        } else {
+          tcgen05_fence_before();  // accumulator fully read: hand the TMEM buffer back to the MMA warp
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         float y[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);
-        if (col0 + 32 <= N) {
-          if (ep.bias) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
-              y[i] += b.x; y[i + 1] += b.y; y[i + 2] += b.z; y[i + 3] += b.w;
-            }
-          }
-        } else if (ep.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) y[i] += __ldg(ep.bias + col0 + i);
-        }
-#pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (ACT == ACT_GELU) y[i] = gelu_erf(y[i]);
-          if (ACT == ACT_SILU) y[i] = silu(y[i]);
+          float t = __uint_as_float(v[c & 1][i]);
+          if (ep.bias) t += bv[i];
+          if (ACT == ACT_GELU) t = gelu_erf(t);
+          if (ACT == ACT_SILU) t = silu(t);
+          y[i] = t;
         }
         if (ep.gamma) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (col0 + i < N) y[i] *= __ldg(ep.gamma + col0 + i);
         }
-        // staging buffer `buf` was last read by the TMA store issued two chunks ago
-        if (issuer) tma_store_wait_read<1>();
-        named_bar_sync(bar_id, 128);
-        uint8_t* dst = stg[buf];
+        // this warp's staging buffer `buf` was last read by the TMA store it issued two chunks ago
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* dst = stg + buf * Cfg::kWarpStagingBytes;
         if constexpr (OUT_F32) {
           // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + r * 128 + ((j ^ (r & 7)) << 4)) =
+            *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                 make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         } else {
           // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
@@ -225,12 +232,12 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
             __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
             for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
-            *reinterpret_cast<uint4*>(dst + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = pk;
+            *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
           }
         }
         fence_proxy_async_smem();
-        named_bar_sync(bar_id, 128);
-        if (issuer) {
+        __syncwarp();
+        if (lane == 0) {
           if (REDUCE) tma_reduce_add_2d(&tma_c, dst, col0, m0);
           else tma_store_2d(&tma_c, dst, col0, m0);
           tma_store_commit();
@@ -238,7 +245,7 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
         buf ^= 1;
       }
     }
-    if (issuer) tma_store_wait_all<0>();  // global writes complete before the CTA exits
+    if (lane == 0) tma_store_wait_all<0>();  // global writes complete before the CTA exits
   }
   tcgen05_fence_before();
   __syncthreads();

@@ -1,0 +1,139 @@
+"""CPU: the oracle restatements against (a) the committed golden fixtures generated from the live
+reference (oracle/make_golden.py) and (b) the live reference itself when /root/reference is present."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import knn as OK, make_golden as MG, ref_harness as rh, transform as OT, vit as OV, yolo as OY
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+needs_ref = pytest.mark.skipif(not rh.available(), reason="/root/reference absent (GPU box)")
+
+
+def test_transform_matches_golden():
+    g = np.load(GOLDEN / "transform_golden.npz")
+    for i, crop in enumerate(MG.transform_inputs()):
+        out = OT.paired_transform(crop)
+        assert np.abs(out[:, ::7, ::7] - g[f"sub_{i}"]).max() <= 2e-6
+        assert abs(out.astype(np.float64).sum() - float(g[f"sum_{i}"])) <= 1e-2
+
+
+def test_transform_empty_crop_raises():
+    with pytest.raises(ValueError):
+        OT.paired_transform(np.zeros((64, 0, 3), np.uint8))
+
+
+def test_crop_rects():
+    # banker's rounding + double clipping (infer_effocr.py:286-291)
+    assert OT.crop_rect_torch_path([10.5, 3.2, 21.5, 40.0], 64, 1024) == (10, 0, 22, 64)
+    assert OT.crop_rect_torch_path([10.5, 3.5, 21.5, 40.5], 64, 1024, vertical=True) == (0, 4, 1024, 40)
+    # onnx path: torch.round, x scaled by W/640 in double, full height (infer_effocr_onnx_multi.py:311-318)
+    assert OT.crop_rect_onnx_path([100.4, 1, 120.6, 60], 64, 1024) == (160, 0, 194, 64)
+
+
+@needs_ref
+def test_transform_matches_live_reference():
+    t = rh.import_reference("utils.datasets_utils").create_paired_transform()
+    rng = np.random.default_rng(5)
+    for (h, w) in [(64, 31), (17, 90), (400, 260)]:
+        crop = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.abs(t(crop).numpy() - OT.paired_transform(crop)).max() <= 2e-6
+
+
+def test_vit_matches_golden_reference_hf_backend():
+    sd, x = MG.vit_golden_inputs()
+    with torch.no_grad():
+        e = OV.vit_forward(sd, x).numpy()
+    ref = np.load(GOLDEN / "vit_tiny_golden.npz")["emb"]
+    assert np.linalg.norm(e - ref) / np.linalg.norm(ref) <= 5e-6
+
+
+def test_vit_matches_torchvision():
+    from torchvision.models.vision_transformer import VisionTransformer
+    name = "vit_tiny_patch16_224"
+    sd = OV.randomize_affine(OV.init_vit_state_dict(name, seed=2))
+    d, h, depth, mlp = OV.VIT_CONFIGS[name]
+    tv = VisionTransformer(224, 16, depth, h, d, mlp)
+    tv.heads = torch.nn.Identity()
+    tv.load_state_dict(OV.timm_to_torchvision(sd), strict=True)
+    tv.eval()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        a, b = OV.vit_forward(sd, x), tv(x)
+    assert ((a - b).norm() / b.norm()).item() <= 5e-6
+
+
+def test_vit_key_maps_roundtrip():
+    sd = OV.init_vit_state_dict("vit_tiny_patch16_224", seed=0)
+    back = OV.hf_to_timm(OV.timm_to_hf(sd))
+    assert list(back) == list(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_knn_oracle_ties_and_padding():
+    xb = torch.eye(4)[[0, 1, 1, 2]]  # ids 1 and 2 identical
+    q = torch.tensor([[0.0, 1.0, 0.0, 0.0]])
+    d, i = OK.flat_ip_search(xb, q, 6)
+    assert i[0].tolist() == [1, 2, 0, 3, -1, -1]
+    assert d[0, 4].item() < -3e38
+
+
+def test_index_file_roundtrip(tmp_path):
+    xb = np.random.default_rng(0).normal(size=(7, 5)).astype(np.float32)
+    OK.write_index_flat_ip(tmp_path / "ref.index", xb)
+    assert np.array_equal(OK.read_index_flat_ip(tmp_path / "ref.index"), xb)
+    # the product's reader/writer agree with the oracle's statement of the layout
+    from effocr_b200 import knn as PK
+    idx = PK.read_index(tmp_path / "ref.index")
+    assert idx.ntotal == 7 and idx.d == 5 and np.array_equal(idx.reconstruct_n(), xb)
+    PK.write_index(idx, tmp_path / "ref2.index")
+    assert (tmp_path / "ref2.index").read_bytes() == (tmp_path / "ref.index").read_bytes()
+
+
+def test_nms_matches_golden():
+    g = np.load(GOLDEN / "nms_golden.npz")
+    for i, (pred, conf, iou) in enumerate(MG.nms_inputs()):
+        out = OY.non_max_suppression(pred.clone(), conf_thres=conf, iou_thres=iou, max_det=1000)[0].numpy()
+        assert out.shape == g[f"out_{i}"].shape and np.array_equal(out, g[f"out_{i}"])
+
+
+def test_letterbox_matches_golden():
+    g = np.load(GOLDEN / "letterbox_golden.npz")
+    for i, im in enumerate(MG.letterbox_inputs()):
+        x = OY.load_localizer_img_from_array(im)  # [1,3,640,640] RGB/255
+        u8 = np.rint(x[0][::-1].transpose(1, 2, 0) * 255).astype(np.uint8)  # back to BGR HWC u8
+        assert np.array_equal(u8[::9, ::9], g[f"sub_{i}"])
+        assert int(u8.astype(np.int64).sum()) == int(g[f"sum_{i}"])
+
+
+def test_yolov5s_analytic_invariants():
+    assert OY.count_parameters(OY.init_yolov5s_state_dict(nc=80)) == 7_235_389  # ultralytics yolov5s
+    sd = OY.init_yolov5s_state_dict(nc=2)
+    x = torch.rand(1, 3, 64, 1024, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        o32 = OY.yolov5s_forward(sd, x)
+        o64 = OY.yolov5s_forward(sd, x, dtype=torch.float64)
+    assert o32.shape == (1, 3 * (8 * 128 + 4 * 64 + 2 * 32), 7)
+    assert ((o32 - o64).abs().max() / o64.abs().max()).item() < 1e-5
+    assert 3 * (80 * 80 + 40 * 40 + 20 * 20) == 25200  # prediction count at 640 x 640
+
+
+def test_textproc_matches_golden():
+    from effocr_b200 import textproc as tp
+    recs = json.loads((GOLDEN / "textproc_golden.json").read_text())
+    for c, r in zip(MG.textproc_cases(), recs):
+        chars, words = torch.tensor(c["chars"]), torch.tensor(c["words"]).reshape(-1, 4)
+        sc, wei = tp.en_preprocess(chars, words)
+        assert wei == r["word_end_idx"] and [float(b[0]) for b in sc] == r["order_x0"]
+        assert [float(b[1]) for b in tp.jp_preprocess(chars, vertical=True)] == r["jp_order_y0"]
+        for am in (None, 0.1, 0.3):
+            assert tp.en_postprocess(c["text"], wei, c["heights"], c["bottoms"], anchor_margin=am) == r["post"][str(am)]
+
+
+def test_edit_distance_and_cer():
+    from effocr_b200 import textproc as tp
+    assert tp.edit_distance("kitten", "sitting") == 3 and tp.edit_distance("", "abc") == 3
+    acc, cer = tp.textline_evaluation([("hello world", "hello world"), ("abc", "abd")])
+    assert acc == 50.0 and abs(cer - 1 / 14) < 1e-12
