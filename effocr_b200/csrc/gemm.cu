@@ -95,8 +95,46 @@ static int launch_tma(const GemmArgs& a, cudaStream_t stream) {
   return EFFOCR_OK;
 }
 
+// A-stationary schedule: K <= 384 and at least two N tiles per row block
+template <int BN, int ACT, bool F32, bool RED>
+static int launch_astat(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmAStatCfg<BN, F32>;
+  CUtensorMap ta, tb, tc;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN));
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, 32, 32, F32 ? 128 : 64));
+  auto kern = gemm_tn_astat_kernel<BN, ACT, F32, RED>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_m = (a.M + kBlockM - 1) / kBlockM;
+  const int grid = num_m < sm_count() ? num_m : sm_count();
+  EpiTmaParams ep;
+  ep.bias = a.bias;
+  ep.gamma = a.gamma;
+  {
+    KernelScope ks(a.prof_tag, stream);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+static bool use_astat(int bn, const GemmArgs& a) {
+  if (a.epilogue == 2) return false;
+  const int num_n = (a.N + bn - 1) / bn;
+  const int num_m = (a.M + kBlockM - 1) / kBlockM;
+  return a.K <= 384 && num_n >= 2 && (bn == 192 || bn == 256) && num_m >= 2 * sm_count();
+}
+
 template <int ACT, bool F32, bool RED>
 static int launch_tma_bn(int bn, const GemmArgs& a, cudaStream_t stream) {
+  if (use_astat(bn, a)) {
+    if (bn == 192) return launch_astat<192, ACT, F32, RED>(a, stream);
+    return launch_astat<256, ACT, F32, RED>(a, stream);
+  }
   switch (bn) {
     case 64: return launch_tma<64, ACT, F32, RED>(a, stream);
     case 128: return launch_tma<128, ACT, F32, RED>(a, stream);
@@ -186,6 +224,6 @@ extern "C" int effocr_gemm_f16(const void* A, long long lda, const void* W, long
   a.bias = bias; a.gamma = gamma; a.resid = resid; a.ldr = ldr;
   a.out = out; a.ldo = ldo; a.act = act; a.out_f32 = out_f32;
   a.block_n = block_n & 0xffff;
-  a.epilogue = (block_n >> 16) & 1;  // bit 16 forces the direct-store epilogue (tests compare both)
+  a.epilogue = (block_n >> 16) & 3;  // 1: force the direct-store epilogue, 2: TMA epilogue without the A-stationary schedule
   return effocr::gemm_f16(a, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -62,6 +62,93 @@ struct EpiTmaParams {
   const float* gamma;  // [N] or nullptr
 };
 
+
+// Epilogue of ONE output tile for ONE epilogue warp (TMEM lane quarter q, column half `half`).
+template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE, int NBUF = 2>
+__device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, const EpiTmaParams& ep, uint32_t tmem_base,
+                                                  uint64_t* tfull_bar, uint64_t* tempty_bar, int as, uint32_t aphase,
+                                                  int tile_m0, int tile_n0, int N, int q, int half, int lane,
+                                                  uint8_t* stg, int warp_stg_bytes, int& buf) {
+  constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per half
+  const int m0 = tile_m0 + q * 32;
+  const int n0 = tile_n0 + half * (BLOCK_N / 2);
+  const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
+  mbar_wait(&tfull_bar[as], aphase);
+  tcgen05_fence_after();
+  uint32_t v[2][32];
+  tmem_ld_32x32b_x32(tbase, v[0]);
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col0 = n0 + c * 32;
+    // bias for this chunk: issued before the TMEM wait so both latencies overlap
+    float bv[32];
+    const bool full = (col0 + 32 <= N);
+    if (ep.bias) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+          bv[i] = b.x; bv[i + 1] = b.y; bv[i + 2] = b.z; bv[i + 3] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) bv[i] = (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
+      }
+    }
+    tmem_ld_wait();
+    if (c + 1 < CHUNKS) {
+      tmem_ld_32x32b_x32(tbase + (c + 1) * 32, v[(c + 1) & 1]);  // prefetch the next chunk
+    } else {
+      tcgen05_fence_before();  // accumulator fully read: hand the TMEM buffer back to the MMA warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    float y[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float t = __uint_as_float(v[c & 1][i]);
+      if (ep.bias) t += bv[i];
+      if (ACT == ACT_GELU) t = gelu_erf(t);
+      if (ACT == ACT_SILU) t = silu(t);
+      y[i] = t;
+    }
+    if (ep.gamma) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (col0 + i < N) y[i] *= __ldg(ep.gamma + col0 + i);
+    }
+    // this warp's staging buffer `buf` was last read by the TMA store it issued NBUF chunks ago
+    if (lane == 0) tma_store_wait_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* dst = stg + buf * warp_stg_bytes;
+    if constexpr (OUT_F32) {
+      // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+            make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+    } else {
+      // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 pk;
+        __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+        *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (REDUCE) tma_reduce_add_2d(&tma_c, dst, col0, m0);
+      else tma_store_2d(&tma_c, dst, col0, m0);
+      tma_store_commit();
+    }
+    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
+}
+
 // ACT: activation; OUT_F32: output element type; REDUCE: TMA reduce-add into the output (in-place residual)
 template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -160,92 +247,163 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
     // alone: private double-buffered staging tile, private TMA stores -- no cross-warp barriers.
     const int q = warp_idx & 3;
     const int half = (warp_idx - 4) >> 2;
-    constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per half
     uint8_t* stg = smem_c + (warp_idx - 4) * 2 * Cfg::kWarpStagingBytes;
     int buf = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
-      const int m0 = (tile / num_n) * kBlockM + q * 32;
-      const int n0 = (tile % num_n) * BLOCK_N + half * (BLOCK_N / 2);
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
-      mbar_wait(&tfull_bar[as], aphase);
-      tcgen05_fence_after();
-      uint32_t v[2][32];
-      tmem_ld_32x32b_x32(tbase, v[0]);
-#pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = n0 + c * 32;
-        // bias for this chunk: issued before the TMEM wait so both latencies overlap
-        float bv[32];
-        const bool full = (col0 + 32 <= N);
-        if (ep.bias) {
-          if (full) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
-              bv[i] = b.x; bv[i + 1] = b.y; bv[i + 2] = b.z; bv[i + 3] = b.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) bv[i] = (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
-          }
-        }
-        tmem_ld_wait();
-        if (c + 1 < CHUNKS) {
-          tmem_ld_32x32b_x32(tbase + (c + 1) * 32, v[(c + 1) & 1]);  // prefetch the next chunk
-        } else {
-          tcgen05_fence_before();  // accumulator fully read: hand the TMEM buffer back to the MMA warp
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
-        }
-        float y[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float t = __uint_as_float(v[c & 1][i]);
-          if (ep.bias) t += bv[i];
-          if (ACT == ACT_GELU) t = gelu_erf(t);
-          if (ACT == ACT_SILU) t = silu(t);
-          y[i] = t;
-        }
-        if (ep.gamma) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < N) y[i] *= __ldg(ep.gamma + col0 + i);
-        }
-        // this warp's staging buffer `buf` was last read by the TMA store it issued two chunks ago
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        uint8_t* dst = stg + buf * Cfg::kWarpStagingBytes;
-        if constexpr (OUT_F32) {
-          // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row r lives at chunk j ^ (r & 7)
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(dst + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        } else {
-          // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
-            *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
-          }
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (REDUCE) tma_reduce_add_2d(&tma_c, dst, col0, m0);
-          else tma_store_2d(&tma_c, dst, col0, m0);
-          tma_store_commit();
-        }
-        buf ^= 1;
-      }
+      tma_epilogue_tile<BLOCK_N, ACT, OUT_F32, REDUCE>(tma_c, ep, tmem_base, tfull_bar, tempty_bar, as, aphase,
+                                                        (tile / num_n) * kBlockM, (tile % num_n) * BLOCK_N, N, q, half, lane,
+                                                        stg, Cfg::kWarpStagingBytes, buf);
     }
     if (lane == 0) tma_store_wait_all<0>();  // global writes complete before the CTA exits
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+
+// ------------------------------------------------------------------ A-stationary variant (K <= 384)
+// With K = 384 a 128 x BLOCK_N tile re-reads its 96 KB A block for every N tile, and the kernel runs
+// at the L2 -> SM bandwidth cap (measured: ~13 TB/s of TMA traffic at 55 % tensor-pipe activity).
+// Here a CTA walks ALL N tiles of one 128-row block before moving on, keeping the A block (up to six
+// 16 KB k-blocks) resident in shared memory and streaming only the weight tiles, which cuts operand
+// traffic per tile from (A + B) to B.  A k-block slot j is released for the next row block as soon as
+// the last N tile's MMAs on it retire, so the refill overlaps the tail of the current block.
+template <int BLOCK_N, bool OUT_F32>
+struct GemmAStatCfg {
+  static constexpr int kMaxKB = 6;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kWarpStagingBytes = 32 * 32 * (OUT_F32 ? 4 : 2);
+  static constexpr int kNumBuf = OUT_F32 ? 1 : 2;  // fp32 tiles are single-buffered to leave room for the A block
+  static constexpr int kStagingTotal = 8 * kNumBuf * kWarpStagingBytes;
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kStagesRaw = (kSmemLimit - 1024 - kBarrierBytes - kStagingTotal - kMaxKB * kABytes) / kBBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kMaxKB * kABytes + kStages * kBBytes + kStagingTotal + kBarrierBytes + 1024;
+  static constexpr int kTmemCols = GemmCfg<BLOCK_N>::kTmemCols;
+  static_assert(kStages >= 3, "pipeline too shallow");
+};
+
+template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                     const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiTmaParams ep) {
+  using Cfg = GemmAStatCfg<BLOCK_N, OUT_F32>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int MAXKB = Cfg::kMaxKB;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + MAXKB * Cfg::kABytes;
+  uint8_t* smem_c = smem_b + STAGES * Cfg::kBBytes;
+  uint64_t* bfull_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStagingTotal);
+  uint64_t* bempty_bar = bfull_bar + STAGES;
+  uint64_t* afull_bar = bempty_bar + STAGES;
+  uint64_t* aempty_bar = afull_bar + MAXKB;
+  uint64_t* tfull_bar = aempty_bar + MAXKB;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
+    for (int i = 0; i < MAXKB; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + kBlockM - 1) / kBlockM;
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;  // <= MAXKB (host checks)
+
+  if (warp_idx == 0) {
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t a_phase = 0;  // one A-ring revolution per row block
+      for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x, a_phase ^= 1) {
+        const int m0 = mb * kBlockM;
+        for (int nb = 0; nb < num_n; ++nb) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            if (nb == 0) {
+              mbar_wait(&aempty_bar[kb], a_phase ^ 1);
+              mbar_arrive_expect_tx(&afull_bar[kb], Cfg::kABytes);
+              tma_load_2d(&tma_a, &afull_bar[kb], smem_a + kb * Cfg::kABytes, kb * kBlockK, m0);
+            }
+            mbar_wait(&bempty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&bfull_bar[stage], Cfg::kBBytes);
+            tma_load_2d(&tma_b, &bfull_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK, nb * BLOCK_N);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t a_phase = 0;
+      int local = 0;
+      for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x, a_phase ^= 1) {
+        for (int nb = 0; nb < num_n; ++nb, ++local) {
+          const int as = local & 1;
+          const uint32_t aphase = (local >> 1) & 1;
+          mbar_wait(&tempty_bar[as], aphase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            if (nb == 0) mbar_wait(&afull_bar[kb], a_phase);
+            mbar_wait(&bfull_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + kb * Cfg::kABytes));
+            const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            umma_commit(&bempty_bar[stage]);
+            if (nb == num_n - 1) umma_commit(&aempty_bar[kb]);  // A k-block free for the next row block
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&tfull_bar[as]);
+        }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 4) >> 2;
+    uint8_t* stg = smem_c + (warp_idx - 4) * Cfg::kNumBuf * Cfg::kWarpStagingBytes;
+    int buf = 0;
+    int local = 0;
+    for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x) {
+      for (int nb = 0; nb < num_n; ++nb, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        tma_epilogue_tile<BLOCK_N, ACT, OUT_F32, REDUCE, Cfg::kNumBuf>(tma_c, ep, tmem_base, tfull_bar, tempty_bar, as, aphase,
+                                                          mb * kBlockM, nb * BLOCK_N, N, q, half, lane, stg,
+                                                          Cfg::kWarpStagingBytes, buf);
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tcgen05_fence_before();
   __syncthreads();

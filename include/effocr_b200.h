@@ -63,7 +63,7 @@ EFFOCR_API int effocr_profile_read(int tag, long long* launches, double* total_m
  * onnx_engines/recognizer_engine.py:27 / localizer_engine.py:54.
  * act: 0 none, 1 GELU(erf), 2 SiLU.  out_f32: element type of out and resid (0 fp16, 1 fp32).
  * block_n: 0 = auto, else 64/128/192/256 (| 0x10000 forces the direct-store epilogue instead of the
- * TMA-store / TMA-reduce one).  bias/gamma fp32 [N] or NULL; resid may alias out (in-place update). */
+ * TMA-store / TMA-reduce one, | 0x20000 keeps the TMA epilogue but disables the A-stationary schedule).  bias/gamma fp32 [N] or NULL; resid may alias out (in-place update). */
 EFFOCR_API int effocr_gemm_f16(const void* d_A, long long lda, const void* d_W, long long ldw, int M, int N, int K,
                     const float* d_bias, const float* d_gamma, const void* d_resid, long long ldr, void* d_out,
                     long long ldo, int act, int out_f32, int block_n, void* stream);

@@ -21,6 +21,9 @@ def _rel(a, b):
     (4000, 256, 288, 2, 0, True, False, 0),
     (3000, 21, 512, 0, 1, False, False, 64),
     (20000, 1152, 384, 0, 0, False, False, 0),   # many tiles per CTA: phase wrap of both pipelines
+    (50000, 1152, 384, 0, 0, False, False, 0),   # A-stationary schedule (K <= 384, >= 2 row blocks per SM)
+    (45000, 1536, 384, 1, 0, False, False, 0),
+    (40000, 600, 320, 2, 0, False, False, 0),    # A-stationary with ragged N and K tail
 ])
 @pytest.mark.parametrize("direct", [False, True])
 def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn, direct):
@@ -50,7 +53,7 @@ def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn, direct):
 
 @pytest.mark.parametrize("direct", [False, True])
 @pytest.mark.parametrize("M,N,K,gamma", [(2000, 384, 384, False), (5000, 384, 1536, False), (1333, 96, 384, True),
-                                          (4100, 768, 3072, True)])
+                                          (4100, 768, 3072, True), (60000, 384, 384, False)])
 def test_gemm_inplace_residual(M, N, K, gamma, direct):
     """x <- x + (a @ w.T + bias) * gamma: TMA reduce-add epilogue vs the direct read-modify-write one."""
     from effocr_b200 import ops

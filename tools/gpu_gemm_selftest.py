@@ -90,3 +90,19 @@ if allok:
             ms = e0.elapsed_time(e1) / 10
             print(json.dumps(dict(perf=True, M=M, N=N, K=K, act=act, f32=f32, direct=bool(direct), ms=ms, tflops=2.0 * M * N * K / ms / 1e9)), flush=True)
 print("ALL_OK" if allok else "FAILED", flush=True)
+# A-stationary vs plain TMA-epilogue schedule
+for (M, N, K, act, f32, res) in [(201728, 1152, 384, 0, 0, False), (201728, 1536, 384, 1, 0, False), (201728, 384, 384, 0, 1, True)]:
+    A = (torch.randn(M, K, device=dev) * 0.5).half(); W = (torch.randn(N, K, device=dev) * 0.05).half()
+    b = torch.randn(N, device=dev); odt = torch.float32 if f32 else torch.float16
+    out = torch.zeros(M, N, device=dev, dtype=odt); R = out if res else None
+    for flag in (0, 0x20000):
+        def go():
+            _lib.check(lib.effocr_gemm_f16(A.data_ptr(), K, W.data_ptr(), K, M, N, K, b.data_ptr(), 0, _lib.ptr(R), N,
+                                           out.data_ptr(), N, act, f32, flag, _lib.stream_ptr()))
+        for _ in range(3): go()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): go()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(json.dumps(dict(perf2=True, M=M, N=N, K=K, act=act, f32=f32, astat=(flag == 0), ms=ms, tflops=2.0 * M * N * K / ms / 1e9)), flush=True)
