@@ -51,6 +51,11 @@ SIGNATURES = {
     "effocr_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_int,
                                  c_void_p]),
     "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "effocr_yolo_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "effocr_yolo_destroy": (None, [c_void_p]),
+    "effocr_yolo_num_predictions": (c_int, [c_int, c_int]),
+    "effocr_yolo_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p]),
     "effocr_l2_normalize": (c_int, [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
     "effocr_knn_create": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "effocr_knn_destroy": (None, [c_void_p]),

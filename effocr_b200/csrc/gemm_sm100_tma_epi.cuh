@@ -207,6 +207,13 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m0 = (tile / num_n) * kBlockM;
         const int n0 = (tile % num_n) * BLOCK_N;
+        {  // pull the A block of this CTA's NEXT tile from HBM into L2 while this tile computes
+          const int nt = tile + gridDim.x;
+          if (nt < num_tiles && nt / num_n != tile / num_n) {
+            const int pm0 = (nt / num_n) * kBlockM;
+            for (int kb = 0; kb < num_kb && kb < 24; ++kb) tma_prefetch_l2_2d(&tma_a, kb * kBlockK, pm0);
+          }
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -342,6 +349,8 @@ gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       uint32_t a_phase = 0;  // one A-ring revolution per row block
       for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x, a_phase ^= 1) {
         const int m0 = mb * kBlockM;
+        if (mb + static_cast<int>(gridDim.x) < num_m)  // next row block of this CTA: HBM -> L2 now
+          for (int kb = 0; kb < num_kb; ++kb) tma_prefetch_l2_2d(&tma_a, kb * kBlockK, m0 + gridDim.x * kBlockM);
         for (int nb = 0; nb < num_n; ++nb) {
           for (int kb = 0; kb < num_kb; ++kb) {
             if (nb == 0) {

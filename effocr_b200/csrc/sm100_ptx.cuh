@@ -93,6 +93,12 @@ __device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint64_t*
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// Warm L2 with a box that a later tma_load_2d will fetch (HBM latency moves off the critical path).
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // L2 eviction-policy constants (same encodings CUTLASS' TMA::CacheHintSm90 uses).
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;

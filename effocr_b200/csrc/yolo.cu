@@ -1,0 +1,498 @@
+// YOLOv5s character/word localizer (ultralytics v6/7 yolov5s.yaml) as a C-ABI handle.
+// Replaces the onnxruntime session behind EffLocalizer.run
+// (/root/reference/onnx_engines/localizer_engine.py:25-29,49-55): letterboxed f32 [B,3,H,W] image ->
+// decoded predictions f32 [B, 3*(H/8*W/8 + H/16*W/16 + H/32*W/32), 5+nc].
+//
+// Layout: activations are NHWC fp16, so every 1x1 convolution IS the tcgen05 GEMM
+// [pixels, Cin] x [Cout, Cin]^T with the folded-BatchNorm bias and SiLU in its epilogue, and channel
+// concatenation is free: producers write their GEMM output straight into a channel slice of the
+// consumer's buffer (output leading dimension = total channels).  k > 1 convolutions gather an
+// im2col matrix (fp16) and run the same GEMM.  BatchNorm (eps 1e-3) is folded into the fp16
+// weights / fp32 bias on the host at create time.
+#include <math.h>
+
+#include <vector>
+
+#include "../../include/effocr_b200.h"
+#include "gemm.h"
+
+namespace effocr {
+
+// ------------------------------------------------------------------ gather kernels (HBM-bound)
+// layer 0: f32 NCHW image -> im2col rows of Conv(3, 32, k6, s2, p2); col = c*36 + ky*6 + kx (torch
+// weight order), zero-padded from 108 to 112 columns.
+__global__ void __launch_bounds__(256) yolo_im2col0_kernel(const float* __restrict__ img, __half* __restrict__ col,
+                                                           int B, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 14;  // 14 vectors of 8 columns
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int vec = static_cast<int>(i % 14);
+    const long long row = i / 14;
+    const int ox = static_cast<int>(row % Wo);
+    const int oy = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
+    __half v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cidx = vec * 8 + j;
+      float x = 0.f;
+      if (cidx < 108) {
+        const int c = cidx / 36, ky = (cidx % 36) / 6, kx = cidx % 6;
+        const int iy = oy * 2 - 2 + ky, ix = ox * 2 - 2 + kx;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) x = img[((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix];
+      }
+      v[j] = __float2half_rn(x);
+    }
+    *reinterpret_cast<uint4*>(col + row * 112 + vec * 8) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// 3x3, pad 1, stride s: NHWC fp16 (pixel pitch ld_in) -> [B*Ho*Wo, 9*C], column = (ky*3 + kx)*C + c
+__global__ void __launch_bounds__(256) yolo_im2col3_kernel(const __half* __restrict__ in, int ld_in,
+                                                           __half* __restrict__ col, int B, int H, int W, int C,
+                                                           int stride) {
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int vpt = C / 8;
+  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * vpt;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vpt);
+    const int tap = static_cast<int>((i / vpt) % 9);
+    const long long row = i / (static_cast<long long>(vpt) * 9);
+    const int ox = static_cast<int>(row % Wo);
+    const int oy = static_cast<int>((row / Wo) % Ho);
+    const int b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
+    const int iy = oy * stride - 1 + tap / 3, ix = ox * stride - 1 + tap % 3;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + iy) * W + ix) * ld_in + cv * 8);
+    *reinterpret_cast<uint4*>(col + row * (9LL * C) + tap * C + cv * 8) = v;
+  }
+}
+
+// nearest 2x upsample into a channel slice of the consumer's concat buffer
+__global__ void __launch_bounds__(256) yolo_upsample2x_kernel(const __half* __restrict__ in, int ld_in,
+                                                              __half* __restrict__ out, int ld_out, int B, int h, int w,
+                                                              int C) {
+  const int vpt = C / 8;
+  const long long total = static_cast<long long>(B) * (2 * h) * (2 * w) * vpt;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vpt);
+    const long long pix = i / vpt;
+    const int ox = static_cast<int>(pix % (2 * w));
+    const int oy = static_cast<int>((pix / (2 * w)) % (2 * h));
+    const int b = static_cast<int>(pix / (4LL * w * h));
+    const uint4 v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * h + oy / 2) * w + ox / 2) * ld_in + cv * 8);
+    *reinterpret_cast<uint4*>(out + pix * ld_out + cv * 8) = v;
+  }
+}
+
+// SPPF: three chained 5x5 / stride 1 / pad 2 max-pools == window maxima of 5, 9, 13 (clipped at the border).
+// Reads channels [0, C) of the concat buffer, writes [C, 2C), [2C, 3C), [3C, 4C).
+__global__ void __launch_bounds__(256) yolo_sppf_pool_kernel(__half* __restrict__ buf, int ld, int B, int h, int w, int C) {
+  const int vpt = C / 8;
+  const long long total = static_cast<long long>(B) * h * w * vpt;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % vpt);
+    const long long pix = i / vpt;
+    const int x = static_cast<int>(pix % w);
+    const int y = static_cast<int>((pix / w) % h);
+    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m5[4], m9[4], m13[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) m5[j] = m9[j] = m13[j] = ninf;
+    for (int dy = -6; dy <= 6; ++dy) {
+      const int yy = y + dy;
+      if (yy < 0 || yy >= h) continue;
+      for (int dx = -6; dx <= 6; ++dx) {
+        const int xx = x + dx;
+        if (xx < 0 || xx >= w) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + ((static_cast<long long>(b) * h + yy) * w + xx) * ld + cv * 8);
+        const __half2* hv = reinterpret_cast<const __half2*>(&v);
+        const int r = max(abs(dy), abs(dx));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m13[j] = __hmax2(m13[j], hv[j]);
+          if (r <= 4) m9[j] = __hmax2(m9[j], hv[j]);
+          if (r <= 2) m5[j] = __hmax2(m5[j], hv[j]);
+        }
+      }
+    }
+    __half* o = buf + pix * ld + cv * 8;
+    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(m5);
+    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(m9);
+    *reinterpret_cast<uint4*>(o + 3 * C) = *reinterpret_cast<const uint4*>(m13);
+  }
+}
+
+// Detect decode (inference branch of ultralytics Detect.forward): raw[b*ny*nx + y*nx + x, a*no + o] ->
+// out[b, off + (a*ny + y)*nx + x, o];  s = sigmoid(raw); xy = (2s + grid - 0.5) * stride; wh = (2s)^2 * anchor_px.
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, int ldr, float* __restrict__ out,
+                                                          int B, int ny, int nx, int no, int total_preds, int off,
+                                                          float stride, float aw0, float ah0, float aw1, float ah1,
+                                                          float aw2, float ah2) {
+  const long long total = static_cast<long long>(B) * ny * nx * 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(i % 3);
+    const long long pix = i / 3;
+    const int x = static_cast<int>(pix % nx);
+    const int y = static_cast<int>((pix / nx) % ny);
+    const int b = static_cast<int>(pix / (static_cast<long long>(nx) * ny));
+    const float* r = raw + pix * ldr + a * no;
+    float* o = out + (static_cast<long long>(b) * total_preds + off + (static_cast<long long>(a) * ny + y) * nx + x) * no;
+    const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2);
+    const float ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
+    for (int k = 0; k < no; ++k) {
+      const float s = 1.0f / (1.0f + expf(-r[k]));
+      float v = s;
+      if (k == 0) v = (s * 2.0f + (static_cast<float>(x) - 0.5f)) * stride;
+      else if (k == 1) v = (s * 2.0f + (static_cast<float>(y) - 0.5f)) * stride;
+      else if (k == 2) v = (s * 2.0f) * (s * 2.0f) * aw;
+      else if (k == 3) v = (s * 2.0f) * (s * 2.0f) * ah;
+      o[k] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct ConvW {
+  __half* w = nullptr;  // [cout, kdim] fp16, BN folded, k>1: (ky, kx, cin) column order (layer 0: torch order)
+  float* b = nullptr;   // [cout] fp32 folded BN bias
+  int cin = 0, cout = 0, k = 1, s = 1, kdim = 0;
+};
+
+struct Act {
+  __half* p;
+  int ld;
+};
+
+struct YoloHandle {
+  int nc = 2, no = 7, max_batch = 0, max_h = 0, max_w = 0, ldr = 24;
+  std::vector<ConvW> convs;
+  __half* det_w[3] = {nullptr, nullptr, nullptr};
+  float* det_b[3] = {nullptr, nullptr, nullptr};
+  float anchors_px[3][3][2];
+  std::vector<void*> allocs;
+  // workspace
+  __half* col = nullptr;
+  size_t col_elems = 0;
+  __half* arena = nullptr;
+  size_t arena_elems = 0;
+  float* raw = nullptr;
+  size_t raw_elems = 0;
+  ~YoloHandle() {
+    for (void* p : allocs) cudaFree(p);
+  }
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return EFFOCR_OK;
+  }
+};
+
+// conv spec list in graph order (must match effocr_b200/localizer_engine.py::yolo_weight_order)
+struct ConvSpec { int cin, cout, k, s; };
+static void c3_specs(std::vector<ConvSpec>& v, int c1, int c2, int n) {
+  const int c_ = c2 / 2;
+  v.push_back({c1, c_, 1, 1});
+  v.push_back({c1, c_, 1, 1});
+  v.push_back({2 * c_, c2, 1, 1});
+  for (int j = 0; j < n; ++j) {
+    v.push_back({c_, c_, 1, 1});
+    v.push_back({c_, c_, 3, 1});
+  }
+}
+static std::vector<ConvSpec> yolo_specs() {
+  std::vector<ConvSpec> v;
+  v.push_back({3, 32, 6, 2});      // 0
+  v.push_back({32, 64, 3, 2});     // 1
+  c3_specs(v, 64, 64, 1);          // 2
+  v.push_back({64, 128, 3, 2});    // 3
+  c3_specs(v, 128, 128, 2);        // 4
+  v.push_back({128, 256, 3, 2});   // 5
+  c3_specs(v, 256, 256, 3);        // 6
+  v.push_back({256, 512, 3, 2});   // 7
+  c3_specs(v, 512, 512, 1);        // 8
+  v.push_back({512, 256, 1, 1});   // 9 SPPF cv1
+  v.push_back({1024, 512, 1, 1});  // 9 SPPF cv2
+  v.push_back({512, 256, 1, 1});   // 10
+  c3_specs(v, 512, 256, 1);        // 13
+  v.push_back({256, 128, 1, 1});   // 14
+  c3_specs(v, 256, 128, 1);        // 17
+  v.push_back({128, 128, 3, 2});   // 18
+  c3_specs(v, 256, 256, 1);        // 20
+  v.push_back({256, 256, 3, 2});   // 21
+  c3_specs(v, 512, 512, 1);        // 23
+  return v;
+}
+
+static inline int grid_for(long long total) {
+  long long g = (total + 255) / 256;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+struct YoloRun {
+  YoloHandle* h;
+  cudaStream_t s;
+  int B;
+  size_t conv_i = 0;
+  size_t arena_off = 0;
+  int status = EFFOCR_OK;
+
+  Act buf(long long pixels, int C) {
+    Act a{h->arena + arena_off, C};
+    arena_off += static_cast<size_t>(pixels) * C;
+    arena_off = (arena_off + 127) / 128 * 128;
+    if (arena_off > h->arena_elems && status == EFFOCR_OK) status = fail(EFFOCR_ERR_NOMEM, "yolo: activation arena too small");
+    return a;
+  }
+  static Act slice(Act a, int c0) { return Act{a.p + c0, a.ld}; }
+
+  void gemm(const __half* A, int lda, long long rows, const ConvW& cw, Act out, const Act* resid) {
+    if (status) return;
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.W = cw.w; g.ldw = cw.kdim; g.M = static_cast<int>(rows); g.N = cw.cout; g.K = cw.kdim;
+    g.out = out.p; g.ldo = out.ld; g.bias = cw.b; g.act = 2;
+    if (resid) { g.resid = resid->p; g.ldr = resid->ld; }
+    g.prof_tag = PROF_GEMM_OTHER;
+    status = gemm_f16(g, s);
+  }
+  // 1x1 conv + BN + SiLU (+ residual)
+  void conv1(Act in, long long rows, Act out, const Act* resid = nullptr) {
+    const ConvW& cw = h->convs[conv_i++];
+    gemm(in.p, in.ld, rows, cw, out, resid);
+  }
+  // 3x3 conv (stride 1 or 2) + BN + SiLU (+ residual); returns nothing, output dims are the caller's
+  void conv3(Act in, int H, int W, Act out, const Act* resid = nullptr) {
+    const ConvW& cw = h->convs[conv_i++];
+    if (status) return;
+    const int Ho = (H - 1) / cw.s + 1, Wo = (W - 1) / cw.s + 1;
+    const long long rows = static_cast<long long>(B) * Ho * Wo;
+    if (static_cast<size_t>(rows) * cw.kdim > h->col_elems) { status = fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small"); return; }
+    {
+      KernelScope ks(PROF_CONV_IM2COL, s);
+      yolo_im2col3_kernel<<<grid_for(rows * 9 * (cw.cin / 8)), 256, 0, s>>>(in.p, in.ld, h->col, B, H, W, cw.cin, cw.s);
+    }
+    gemm(h->col, cw.kdim, rows, cw, out, resid);
+  }
+  // C3(c1, c2, n, shortcut) at a level with `pix` pixels of size Hl x Wl
+  void c3(Act in, int c2, int n, bool shortcut, int Hl, int Wl, Act out) {
+    const long long pix = static_cast<long long>(B) * Hl * Wl;
+    const int c_ = c2 / 2;
+    const size_t save = arena_off;
+    Act cat = buf(pix, 2 * c_);
+    Act ya = buf(pix, c_), yb = buf(pix, c_), t = buf(pix, c_);
+    // weight order: cv1, cv2, cv3, m.j.cv1, m.j.cv2 -- fetch explicitly
+    const size_t i_cv1 = conv_i, i_cv2 = conv_i + 1, i_cv3 = conv_i + 2, i_m = conv_i + 3;
+    conv_i = i_cv1;
+    Act y = (n == 0) ? slice(cat, 0) : ya;
+    conv1(in, pix, y);                       // cv1
+    conv_i = i_cv2;
+    conv1(in, pix, slice(cat, c_));          // cv2 -> second half of the concat
+    conv_i = i_m;
+    for (int j = 0; j < n; ++j) {
+      conv1(y, pix, t);                      // m.j.cv1
+      Act dst = (j == n - 1) ? slice(cat, 0) : (y.p == ya.p ? yb : ya);
+      conv3(t, Hl, Wl, dst, shortcut ? &y : nullptr);  // m.j.cv2 (+ y)
+      y = dst;
+    }
+    const size_t i_end = conv_i;
+    conv_i = i_cv3;
+    conv1(cat, pix, out);                    // cv3
+    conv_i = i_end;
+    arena_off = save;                        // scratch of this block is dead once cv3 has been enqueued (stream order)
+  }
+};
+
+static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int W, float* pred, cudaStream_t s) {
+  YoloRun r{h, s, B};
+  const int H1 = H / 2, W1 = W / 2, H2 = H / 4, W2 = W / 4, H3 = H / 8, W3 = W / 8, H4 = H / 16, W4 = W / 16, H5 = H / 32,
+            W5 = W / 32;
+  const long long p1 = 1LL * B * H1 * W1, p2 = 1LL * B * H2 * W2, p3 = 1LL * B * H3 * W3, p4 = 1LL * B * H4 * W4,
+                  p5 = 1LL * B * H5 * W5;
+  // long-lived buffers first (never released)
+  Act x0 = r.buf(p1, 32), x1 = r.buf(p2, 64), x2 = r.buf(p2, 64), x3 = r.buf(p3, 128), x5 = r.buf(p4, 256),
+      x7 = r.buf(p5, 512), x8 = r.buf(p5, 512), catS = r.buf(p5, 1024), x9 = r.buf(p5, 512);
+  Act cat12 = r.buf(p4, 512), cat16 = r.buf(p3, 256), cat19 = r.buf(p4, 256), cat22 = r.buf(p5, 512);
+  Act x13 = r.buf(p4, 256), x17 = r.buf(p3, 128), x20 = r.buf(p4, 256), x23 = r.buf(p5, 512);
+  if (r.status) return r.status;
+  // layer 0
+  {
+    const ConvW& cw = h->convs[r.conv_i++];
+    if (static_cast<size_t>(p1) * 112 > h->col_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small");
+    {
+      KernelScope ks(PROF_CONV_IM2COL, s);
+      yolo_im2col0_kernel<<<grid_for(p1 * 14), 256, 0, s>>>(img, h->col, B, H, W);
+    }
+    r.gemm(h->col, 112, p1, cw, x0, nullptr);
+  }
+  r.conv3(x0, H1, W1, x1);                              // 1
+  r.c3(x1, 64, 1, true, H2, W2, x2);                    // 2
+  r.conv3(x2, H2, W2, x3);                              // 3
+  r.c3(x3, 128, 2, true, H3, W3, YoloRun::slice(cat16, 128));   // 4 -> second half of cat16
+  r.conv3(YoloRun::slice(cat16, 128), H3, W3, x5);      // 5
+  r.c3(x5, 256, 3, true, H4, W4, YoloRun::slice(cat12, 256));   // 6 -> second half of cat12
+  r.conv3(YoloRun::slice(cat12, 256), H4, W4, x7);      // 7
+  r.c3(x7, 512, 1, true, H5, W5, x8);                   // 8
+  r.conv1(x8, p5, YoloRun::slice(catS, 0));             // 9 SPPF cv1 -> first quarter of catS
+  if (!r.status) {
+    KernelScope ks(PROF_YOLO_MISC, s);
+    yolo_sppf_pool_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, 1024, B, H5, W5, 256);
+  }
+  r.conv1(catS, p5, x9);                                // 9 SPPF cv2
+  r.conv1(x9, p5, YoloRun::slice(cat22, 256));          // 10 -> second half of cat22
+  if (!r.status) {
+    KernelScope ks(PROF_YOLO_MISC, s);
+    yolo_upsample2x_kernel<<<grid_for(p4 * 32), 256, 0, s>>>(cat22.p + 256, 512, cat12.p, 512, B, H5, W5, 256);  // 11, 12
+  }
+  r.c3(cat12, 256, 1, false, H4, W4, x13);              // 13
+  r.conv1(x13, p4, YoloRun::slice(cat19, 128));         // 14 -> second half of cat19
+  if (!r.status) {
+    KernelScope ks(PROF_YOLO_MISC, s);
+    yolo_upsample2x_kernel<<<grid_for(p3 * 16), 256, 0, s>>>(cat19.p + 128, 256, cat16.p, 256, B, H4, W4, 128);  // 15, 16
+  }
+  r.c3(cat16, 128, 1, false, H3, W3, x17);              // 17
+  r.conv3(x17, H3, W3, YoloRun::slice(cat19, 0));       // 18 -> first half of cat19
+  r.c3(cat19, 256, 1, false, H4, W4, x20);              // 20
+  r.conv3(x20, H4, W4, YoloRun::slice(cat22, 0));       // 21 -> first half of cat22
+  r.c3(cat22, 512, 1, false, H5, W5, x23);              // 23
+  if (r.status) return r.status;
+  // Detect
+  const int total_preds = 3 * (H3 * W3 + H4 * W4 + H5 * W5);
+  const Act feats[3] = {x17, x20, x23};
+  const int chans[3] = {128, 256, 512};
+  const int nys[3] = {H3, H4, H5}, nxs[3] = {W3, W4, W5};
+  const float strides[3] = {8.f, 16.f, 32.f};
+  int off = 0;
+  for (int l = 0; l < 3; ++l) {
+    const long long rows = 1LL * B * nys[l] * nxs[l];
+    if (static_cast<size_t>(rows) * h->ldr > h->raw_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: detect scratch too small");
+    GemmArgs g;
+    g.A = feats[l].p; g.lda = feats[l].ld; g.W = h->det_w[l]; g.ldw = chans[l]; g.M = static_cast<int>(rows);
+    g.N = 3 * h->no; g.K = chans[l]; g.out = h->raw; g.ldo = h->ldr; g.out_f32 = 1; g.bias = h->det_b[l];
+    g.prof_tag = PROF_GEMM_OTHER;
+    EFFOCR_TRY(gemm_f16(g, s));
+    {
+      KernelScope ks(PROF_YOLO_MISC, s);
+      yolo_decode_kernel<<<grid_for(rows * 3), 256, 0, s>>>(h->raw, h->ldr, pred, B, nys[l], nxs[l], h->no, total_preds, off,
+                                                            strides[l], h->anchors_px[l][0][0], h->anchors_px[l][0][1],
+                                                            h->anchors_px[l][1][0], h->anchors_px[l][1][1],
+                                                            h->anchors_px[l][2][0], h->anchors_px[l][2][1]);
+    }
+    off += 3 * nys[l] * nxs[l];
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+}  // namespace effocr
+
+using namespace effocr;
+
+extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, const float* const* h_weights,
+                                  int n_weights, effocr_yolo_t* out) {
+  if (!out) return fail(EFFOCR_ERR_INVALID, "yolo_create: null out");
+  *out = nullptr;
+  EFFOCR_TRY(require_sm100());
+  const std::vector<ConvSpec> specs = yolo_specs();
+  if (n_weights != static_cast<int>(specs.size()) * 5 + 7)
+    return fail(EFFOCR_ERR_INVALID, "yolo_create: expected 5 tensors per conv (w, bn.w, bn.b, bn.mean, bn.var) + 3 x (w, b) + anchors");
+  if (nc < 1 || nc > 80 || max_batch < 1 || max_h % 32 || max_w % 32 || max_h < 32 || max_w < 32)
+    return fail(EFFOCR_ERR_INVALID, "yolo_create: bad nc / batch / input shape (H, W must be multiples of 32)");
+  YoloHandle* h = new YoloHandle();
+  h->nc = nc; h->no = 5 + nc; h->max_batch = max_batch; h->max_h = max_h; h->max_w = max_w;
+  h->ldr = (3 * h->no + 3) / 4 * 4;
+  int st = EFFOCR_OK;
+  for (size_t i = 0; i < specs.size() && !st; ++i) {
+    const ConvSpec& sp = specs[i];
+    const float* w = h_weights[5 * i];
+    const float *g = h_weights[5 * i + 1], *bb = h_weights[5 * i + 2], *mu = h_weights[5 * i + 3], *var = h_weights[5 * i + 4];
+    ConvW cw;
+    cw.cin = sp.cin; cw.cout = sp.cout; cw.k = sp.k; cw.s = sp.s;
+    const int kk = sp.k * sp.k;
+    cw.kdim = (sp.k == 6) ? 112 : sp.cin * kk;
+    std::vector<__half> wh(static_cast<size_t>(sp.cout) * cw.kdim, __float2half_rn(0.f));
+    std::vector<float> bias(sp.cout);
+    for (int o = 0; o < sp.cout; ++o) {
+      const float scale = g[o] / sqrtf(var[o] + 1e-3f);
+      bias[o] = bb[o] - mu[o] * scale;
+      for (int c = 0; c < sp.cin; ++c)
+        for (int t = 0; t < kk; ++t) {
+          const float v = w[(static_cast<size_t>(o) * sp.cin + c) * kk + t] * scale;
+          const size_t col = (sp.k == 6) ? static_cast<size_t>(c) * 36 + t : static_cast<size_t>(t) * sp.cin + c;
+          wh[static_cast<size_t>(o) * cw.kdim + col] = __float2half_rn(v);
+        }
+    }
+    if ((st = h->alloc(&cw.w, wh.size()))) break;
+    if ((st = h->alloc(&cw.b, bias.size()))) break;
+    cudaMemcpy(cw.w, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemcpy(cw.b, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    h->convs.push_back(cw);
+  }
+  const int chans[3] = {128, 256, 512};
+  const float strides[3] = {8.f, 16.f, 32.f};
+  const size_t base = specs.size() * 5;
+  for (int l = 0; l < 3 && !st; ++l) {
+    const float* w = h_weights[base + 2 * l];
+    const float* b = h_weights[base + 2 * l + 1];
+    const int n = 3 * h->no;
+    std::vector<__half> wh(static_cast<size_t>(n) * chans[l]);
+    for (size_t i = 0; i < wh.size(); ++i) wh[i] = __float2half_rn(w[i]);
+    if ((st = h->alloc(&h->det_w[l], wh.size()))) break;
+    if ((st = h->alloc(&h->det_b[l], static_cast<size_t>(h->ldr)))) break;
+    cudaMemcpy(h->det_w[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
+    cudaMemset(h->det_b[l], 0, h->ldr * 4);
+    cudaMemcpy(h->det_b[l], b, n * 4, cudaMemcpyHostToDevice);
+    const float* an = h_weights[base + 6];  // [3,3,2] in stride units (ultralytics buffer `anchors`)
+    for (int a = 0; a < 3; ++a)
+      for (int d = 0; d < 2; ++d) h->anchors_px[l][a][d] = an[(l * 3 + a) * 2 + d] * strides[l];
+  }
+  if (!st) {
+    const size_t px = static_cast<size_t>(max_batch) * max_h * max_w;
+    h->col_elems = px / 4 * 112 + 4096;  // layer 0 dominates: (H/2 * W/2) rows x 112
+    const size_t col2 = px / 16 * 288 + 4096;
+    if (col2 > h->col_elems) h->col_elems = col2;
+    // activation arena: sum of long-lived buffers + the largest C3 scratch, generously rounded
+    h->arena_elems = px * 40 / 4 + px * 2 + (1u << 20);
+    h->raw_elems = px / 64 * h->ldr + 4096;
+    if (!(st = h->alloc(&h->col, h->col_elems)) && !(st = h->alloc(&h->arena, h->arena_elems))) st = h->alloc(&h->raw, h->raw_elems);
+  }
+  if (!st && cudaDeviceSynchronize() != cudaSuccess) st = fail(EFFOCR_ERR_CUDA, "yolo_create: upload failed");
+  if (st) { delete h; return st; }
+  *out = reinterpret_cast<effocr_yolo_t>(h);
+  return EFFOCR_OK;
+}
+
+extern "C" void effocr_yolo_destroy(effocr_yolo_t h) { delete reinterpret_cast<YoloHandle*>(h); }
+
+extern "C" int effocr_yolo_num_predictions(int height, int width) {
+  if (height % 32 || width % 32) return -1;
+  return 3 * ((height / 8) * (width / 8) + (height / 16) * (width / 16) + (height / 32) * (width / 32));
+}
+
+extern "C" int effocr_yolo_forward(effocr_yolo_t handle, const float* d_images, int batch, int height, int width,
+                                   float* d_pred, void* stream) {
+  YoloHandle* h = reinterpret_cast<YoloHandle*>(handle);
+  if (!h || !d_images || !d_pred || batch < 0) return fail(EFFOCR_ERR_INVALID, "yolo_forward: bad arguments");
+  if (height % 32 || width % 32 || height < 32 || width < 32) return fail(EFFOCR_ERR_INVALID, "yolo_forward: H and W must be multiples of 32");
+  if (static_cast<long long>(height) * width > static_cast<long long>(h->max_h) * h->max_w)
+    return fail(EFFOCR_ERR_INVALID, "yolo_forward: image larger than the handle's workspace");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int npred = effocr_yolo_num_predictions(height, width);
+  for (int b0 = 0; b0 < batch; b0 += h->max_batch) {
+    const int B = batch - b0 < h->max_batch ? batch - b0 : h->max_batch;
+    EFFOCR_TRY(yolo_forward_impl(h, d_images + static_cast<size_t>(b0) * 3 * height * width, B, height, width,
+                                 d_pred + static_cast<size_t>(b0) * npred * h->no, s));
+  }
+  return EFFOCR_OK;
+}

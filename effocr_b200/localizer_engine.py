@@ -1,0 +1,243 @@
+"""Drop-in for /root/reference/onnx_engines/localizer_engine.py: `EffLocalizer`.
+
+Same constructor and call surface -- `EffLocalizer(model_path, iou_thresh=0.01, conf_thresh=0.30, vertical=False,
+num_cores=None, providers=None, input_shape=(640, 640), model_backend='yolo')`, `run(imgs)` with `imgs` a list of
+paths or of letterboxed `np.float32[1,3,H,W]` arrays, returning one `Tensor f32[n, 6]` (x1, y1, x2, y2, conf, cls;
+letterbox pixels; confidence-sorted) per image, and the static helpers `letterbox`, `load_localizer_img`,
+`xywh2xyxy`, `box_iou`, `non_max_suppression` -- but the YOLOv5s forward pass and the NMS run in
+csrc/yolo.cu / csrc/nms.cu on the B200 instead of onnxruntime + torchvision on the CPU.
+
+`model_path`: an ultralytics-keyed YOLOv5s state dict (`model.{i}...`; what `best.pt['model'].state_dict()` holds),
+as a dict or a .pth/.pt/.npz path.  ONNX graphs are not parsed.  Only model_backend='yolo' is implemented
+(mmdetection / detectron2 back-ends are out of scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+
+YOLO_CONV_ORDER_C3 = lambda p, n: [p + "cv1.", p + "cv2.", p + "cv3."] + [p + f"m.{j}.cv{k}." for j in range(n) for k in (1, 2)]
+
+
+def yolo_conv_prefixes():
+    """Conv blocks in the order csrc/yolo.cu::yolo_specs() expects."""
+    c3 = YOLO_CONV_ORDER_C3
+    out = ["model.0.", "model.1."] + c3("model.2.", 1) + ["model.3."] + c3("model.4.", 2) + ["model.5."] + c3("model.6.", 3)
+    out += ["model.7."] + c3("model.8.", 1) + ["model.9.cv1.", "model.9.cv2.", "model.10."] + c3("model.13.", 1)
+    out += ["model.14."] + c3("model.17.", 1) + ["model.18."] + c3("model.20.", 1) + ["model.21."] + c3("model.23.", 1)
+    return out
+
+
+def yolo_weight_order():
+    keys = []
+    for p in yolo_conv_prefixes():
+        keys += [p + "conv.weight", p + "bn.weight", p + "bn.bias", p + "bn.running_mean", p + "bn.running_var"]
+    for l in range(3):
+        keys += [f"model.24.m.{l}.weight", f"model.24.m.{l}.bias"]
+    keys.append("model.24.anchors")
+    return keys
+
+
+def _load_state(model):
+    if isinstance(model, dict):
+        sd = model
+    else:
+        path = str(model)
+        if path.endswith(".onnx"):
+            raise _lib.EffocrError("EffLocalizer: pass the YOLOv5s weights as an ultralytics-keyed state dict (.pth); "
+                                   "ONNX graphs are not parsed by effocr_b200")
+        if path.endswith(".npz"):
+            sd = {k: torch.from_numpy(v) for k, v in np.load(path).items()}
+        else:
+            sd = torch.load(path, map_location="cpu", weights_only=False)
+            if isinstance(sd, dict) and "model" in sd and hasattr(sd["model"], "state_dict"):
+                sd = sd["model"].float().state_dict()  # ultralytics best.pt
+    return sd
+
+
+class YoloEngine:
+    """Device-resident YOLOv5s (fp16 NHWC activations, folded BN) behind effocr_yolo_*."""
+
+    def __init__(self, state_dict, max_batch=16, max_shape=(640, 640)):
+        self._lib = _lib.load()
+        _lib.require_device()
+        sd = state_dict
+        self.nc = int(sd["model.24.m.0.bias"].numel() // 3 - 5)
+        self.no = self.nc + 5
+        keys = yolo_weight_order()
+        keep, ptrs = [], (C.c_void_p * len(keys))()
+        for i, k in enumerate(keys):
+            a = np.ascontiguousarray(sd[k].detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+        h = C.c_void_p()
+        _lib.check(self._lib.effocr_yolo_create(self.nc, int(max_batch), int(max_shape[0]), int(max_shape[1]), ptrs, len(keys),
+                                                C.byref(h)), "effocr_yolo_create")
+        self._h = h
+        self._lock = threading.Lock()
+        self.max_batch = max_batch
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.effocr_yolo_destroy(h)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: CUDA f32 [B,3,H,W] -> CUDA f32 [B, npred, 5+nc] decoded predictions."""
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3:
+            raise _lib.EffocrError("YoloEngine.forward expects a CUDA float32 [B,3,H,W] tensor")
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        npred = self._lib.effocr_yolo_num_predictions(H, W)
+        if npred < 0:
+            raise _lib.EffocrError("input height/width must be multiples of 32")
+        out = torch.empty((B, npred, self.no), device=x.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.effocr_yolo_forward(self._h, x.data_ptr(), B, H, W, out.data_ptr(), _lib.stream_ptr()),
+                       "effocr_yolo_forward")
+        return out
+
+
+def nms_device(pred: torch.Tensor, conf_thres: float, iou_thres: float, max_det: int = 1000):
+    """pred CUDA f32 [B, npred, no] -> (out f32 [B, max_det, 6], count i32 [B]) on the device."""
+    lib = _lib.load()
+    if not pred.is_cuda or pred.dtype != torch.float32:
+        raise _lib.EffocrError("nms_device expects a CUDA float32 tensor")
+    pred = pred.contiguous()
+    B, npred, no = pred.shape
+    out = torch.empty((B, max_det, 6), device=pred.device, dtype=torch.float32)
+    cnt = torch.empty((B,), device=pred.device, dtype=torch.int32)
+    _lib.check(lib.effocr_nms(pred.data_ptr(), B, npred, no, float(conf_thres), float(iou_thres), int(max_det), out.data_ptr(),
+                              cnt.data_ptr(), _lib.stream_ptr()), "effocr_nms")
+    return out, cnt
+
+
+class EffLocalizer:
+
+    def __init__(self, model_path, iou_thresh=0.01, conf_thresh=0.30, vertical=False, num_cores=None, providers=None,
+                 input_shape=(640, 640), model_backend="yolo", max_batch=16):
+        if model_backend != "yolo":
+            raise NotImplementedError("Backend {} is not implemented".format(model_backend))
+        self._eng_net = YoloEngine(_load_state(model_path), max_batch=max_batch, max_shape=tuple(input_shape))
+        self._iou_thresh = iou_thresh
+        self._conf_thresh = conf_thresh
+        self._vertical = vertical
+        self._input_shape = tuple(input_shape)
+        self._model_input_shape = [1, 3, "height", "width"]  # dynamic, like an ONNX export with dynamic axes
+        self._model_backend = model_backend
+        self._input_name = "images"
+
+    def __call__(self, imgs):
+        return self.run(imgs)
+
+    def run(self, imgs):
+        if isinstance(imgs, list):
+            if isinstance(imgs[0], str):
+                imgs = [EffLocalizer.load_localizer_img(img, self._input_shape, backend=self._model_backend) for img in imgs]
+        # batch images of equal shape into one forward pass (the reference loops one image at a time)
+        arrs = [np.asarray(i, dtype=np.float32).reshape((-1,) + tuple(np.asarray(i).shape[-3:])) for i in imgs]
+        results = [None] * len(arrs)
+        by_shape = {}
+        for k, a in enumerate(arrs):
+            by_shape.setdefault(a.shape[1:], []).append(k)
+        for shape, idxs in by_shape.items():
+            x = torch.from_numpy(np.concatenate([arrs[k] for k in idxs], 0)).cuda(non_blocking=True)
+            pred = self._eng_net.forward(x)
+            out, cnt = nms_device(pred, self._conf_thresh, self._iou_thresh, max_det=1000)
+            out, cnt = out.cpu(), cnt.cpu().tolist()
+            for j, k in enumerate(idxs):
+                results[k] = out[j, :cnt[j]].clone()
+        return results
+
+    # ---- device-resident variant used by the pipeline: no host round trip of predictions
+    def run_device(self, x: torch.Tensor):
+        pred = self._eng_net.forward(x)
+        return nms_device(pred, self._conf_thresh, self._iou_thresh, max_det=1000)
+
+    # ---- static helpers with the reference's signatures (host pre-processing stays on the host: OpenCV)
+    @staticmethod
+    def get_onnx_input_name(model):
+        return "images"
+
+    @staticmethod
+    def load_localizer_img(input_path, input_shape, backend="yolo"):
+        """localizer_engine.py:75-85."""
+        if backend != "yolo":
+            raise NotImplementedError("Backend {} is not implemented".format(backend))
+        import cv2
+
+        im0 = cv2.imread(input_path)
+        return EffLocalizer.preprocess_bgr(im0, input_shape)
+
+    @staticmethod
+    def preprocess_bgr(im0, input_shape):
+        im = EffLocalizer.letterbox(im0, input_shape, stride=32, auto=False)[0]
+        im = im.transpose((2, 0, 1))[::-1]  # HWC to CHW, BGR to RGB
+        im = np.ascontiguousarray(im).astype(np.float32) / 255.0
+        if im.ndim == 3:
+            im = np.expand_dims(im, 0)
+        return im
+
+    @staticmethod
+    def letterbox(im, new_shape=(640, 640), color=(114, 114, 114), auto=True, scaleFill=False, scaleup=True, stride=32):
+        """localizer_engine.py:107-138 (ultralytics letterbox): resize keeping aspect, pad to new_shape."""
+        import cv2
+
+        shape = im.shape[:2]
+        if isinstance(new_shape, int):
+            new_shape = (new_shape, new_shape)
+        r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+        if not scaleup:
+            r = min(r, 1.0)
+        ratio = r, r
+        new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+        dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+        if auto:
+            dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+        elif scaleFill:
+            dw, dh = 0.0, 0.0
+            new_unpad = (new_shape[1], new_shape[0])
+            ratio = new_shape[1] / shape[1], new_shape[0] / shape[0]
+        dw /= 2
+        dh /= 2
+        if shape[::-1] != new_unpad:
+            im = cv2.resize(im, new_unpad, interpolation=cv2.INTER_LINEAR)
+        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+        im = cv2.copyMakeBorder(im, top, bottom, left, right, cv2.BORDER_CONSTANT, value=color)
+        return im, ratio, (dw, dh)
+
+    @staticmethod
+    def xywh2xyxy(x):
+        y = x.clone() if isinstance(x, torch.Tensor) else np.copy(x)
+        y[:, 0] = x[:, 0] - x[:, 2] / 2
+        y[:, 1] = x[:, 1] - x[:, 3] / 2
+        y[:, 2] = x[:, 0] + x[:, 2] / 2
+        y[:, 3] = x[:, 1] + x[:, 3] / 2
+        return y
+
+    @staticmethod
+    def box_iou(box1, box2, eps=1e-7):
+        (a1, a2), (b1, b2) = box1.unsqueeze(1).chunk(2, 2), box2.unsqueeze(0).chunk(2, 2)
+        inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp(0).prod(2)
+        return inter / ((a2 - a1).prod(2) + (b2 - b1).prod(2) - inter + eps)
+
+    @staticmethod
+    def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                            labels=(), max_det=300, nm=0):
+        """Reference signature; single-label, class-aware path (the only one the reference exercises) on the GPU."""
+        if classes is not None or agnostic or multi_label or labels or nm:
+            raise NotImplementedError("only the default single-label class-aware NMS path is implemented")
+        if isinstance(prediction, (list, tuple)):
+            prediction = prediction[0]
+        assert 0 <= conf_thres <= 1, f"Invalid Confidence threshold {conf_thres}, valid values are between 0.0 and 1.0"
+        assert 0 <= iou_thres <= 1, f"Invalid IoU {iou_thres}, valid values are between 0.0 and 1.0"
+        dev = prediction.device
+        out, cnt = nms_device(torch.as_tensor(prediction, dtype=torch.float32).cuda(), conf_thres, iou_thres, max_det)
+        out, cnt = out.to(dev), cnt.cpu().tolist()
+        return [out[b, :cnt[b]].clone() for b in range(out.shape[0])]

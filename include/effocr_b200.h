@@ -122,6 +122,30 @@ EFFOCR_API int effocr_layernorm(const float* d_x, long long ldx, const float* d_
 /* qkv fp16 [B*197, 3*H*64] (rows [q|k|v], each [H,64]) -> out fp16 [B*197, H*64] */
 EFFOCR_API int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, void* stream);
 
+/* ---- localizer: YOLOv5s forward (ultralytics yolov5s.yaml, nc classes) ---------------------------
+ * Replaces the onnxruntime session behind EffLocalizer.run (onnx_engines/localizer_engine.py:25-29,49-55).
+ * h_weights: HOST fp32 tensors in graph order (n_weights = 57 * 5 + 7): for every Conv block
+ * (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var) in the order layer 0, 1,
+ * C3@2 (cv1, cv2, cv3, m.0.cv1, m.0.cv2), 3, C3@4, 5, C3@6, 7, C3@8, SPPF (cv1, cv2), 10, C3@13, 14, C3@17,
+ * 18, C3@20, 21, C3@23; then Detect m.0.weight, m.0.bias, m.1.*, m.2.*, anchors [3,3,2] (stride units).
+ * BatchNorm (eps 1e-3) is folded at create.  d_images: fp32 [B,3,H,W] RGB in [0,1] (the letterboxed
+ * tensor EffLocalizer.load_localizer_img builds), H and W multiples of 32 with H*W <= max_h*max_w.
+ * d_pred: fp32 [B, effocr_yolo_num_predictions(H, W), 5+nc] = (cx, cy, w, h, obj, cls...) in input pixels. */
+typedef struct effocr_yolo_s* effocr_yolo_t;
+EFFOCR_API int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, const float* const* h_weights,
+                                  int n_weights, effocr_yolo_t* out);
+EFFOCR_API void effocr_yolo_destroy(effocr_yolo_t h);
+EFFOCR_API int effocr_yolo_num_predictions(int height, int width);
+EFFOCR_API int effocr_yolo_forward(effocr_yolo_t h, const float* d_images, int batch, int height, int width,
+                                   float* d_pred, void* stream);
+
+/* ---- K9: confidence filter + class-aware greedy NMS ---------------------------------------------
+ * Replaces EffLocalizer.non_max_suppression incl. torchvision.ops.nms (localizer_engine.py:171-277):
+ * obj > conf -> conf = obj * cls -> best class, conf > thr -> sort by conf desc -> boxes offset by cls*7680 ->
+ * drop IoU > iou_thres -> first max_det.  d_out: fp32 [B, max_det, 6] (x1,y1,x2,y2,conf,cls), d_count: int [B]. */
+EFFOCR_API int effocr_nms(const float* d_pred, int batch, int npred, int no, float conf_thres, float iou_thres,
+                          int max_det, float* d_out, int* d_count, void* stream);
+
 /* ---- a9: row-wise L2 normalisation, x / max(||x||, eps) -------------------------------------
  * Replaces torch.nn.functional.normalize at infer_effocr.py:316 / infer_effocr_onnx_multi.py:371. */
 EFFOCR_API int effocr_l2_normalize(const float* d_x, float* d_out, int rows, int dim, float eps, void* stream);
