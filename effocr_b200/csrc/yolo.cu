@@ -462,8 +462,9 @@ extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, c
     h->col_elems = px / 4 * 112 + 4096;  // layer 0 dominates: (H/2 * W/2) rows x 112
     const size_t col2 = px / 16 * 288 + 4096;
     if (col2 > h->col_elems) h->col_elems = col2;
-    // activation arena: sum of long-lived buffers + the largest C3 scratch, generously rounded
-    h->arena_elems = px * 40 / 4 + px * 2 + (1u << 20);
+    // activation arena: long-lived buffers (33.5 elements per input pixel) + the largest C3 scratch
+    // (10 per pixel, at stride 4) + per-buffer 128-element rounding
+    h->arena_elems = px * 48 + (1u << 20);
     h->raw_elems = px / 64 * h->ldr + 4096;
     if (!(st = h->alloc(&h->col, h->col_elems)) && !(st = h->alloc(&h->arena, h->arena_elems))) st = h->alloc(&h->raw, h->raw_elems);
   }

@@ -1,0 +1,134 @@
+"""Line-image -> transcription orchestration: the B200-first counterpart of the reference's two drivers
+
+  * `run_effocr(...)`      /root/reference/infer_effocr_onnx_multi.py:227-397  (YOLO + ViT + kNN, k = 1)
+  * `EffOCR.infer(...)`    /root/reference/infer_effocr.py:257-343            (per line, k = self.knn)
+
+The reference runs three globally barriered thread-pool phases (localize, transform, recognize) with four
+host round trips per line.  Here every batch of lines makes ONE pass:
+
+    host: letterbox (OpenCV, as the reference)            -> H2D  f32 [B,3,H,W]  + u8 line pixels
+    GPU : YOLOv5s forward -> NMS                          -> D2H  boxes [B, <=1000, 6] (a few KB)
+    host: per-line box ordering / word segmentation / crop-rectangle arithmetic (exact reference semantics)
+                                                          -> H2D  crop rectangles (20 B each)
+    GPU : fused crop+resize+normalise -> ViT -> L2 norm -> exact kNN
+                                                          -> D2H  k ids (+ distances) per character
+    host: id -> char decode, en_postprocess
+
+Pixels, crops, embeddings and scores never leave the device.  Results are keyed and ordered by input, so they
+are independent of batch composition and of how lines are sharded over ranks.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops, textproc
+from .localizer_engine import EffLocalizer
+from .pipeline import PackedCrops, RecognizerPipeline
+
+
+def crop_rect_onnx_path(bbox, im_height: int, im_width: int, vertical: bool):
+    """infer_effocr_onnx_multi.py:311-318: torch.round (half-to-even) on the letterbox-space box, rescale the
+    text-direction axis by (image extent / 640) in Python floats, int(round(.)), full extent on the other axis."""
+    x0, y0, x1, y1 = torch.round(torch.as_tensor(bbox[:4], dtype=torch.float32))
+    if vertical:
+        return 0, int(round(y0.item() * im_height / 640)), im_width, int(round(y1.item() * im_height / 640))
+    return int(round(x0.item() * im_width / 640)), 0, int(round(x1.item() * im_width / 640)), im_height
+
+
+def crop_rect_torch_path(bbox, im_height: int, im_width: int, vertical: bool, double_clipped: bool = True):
+    """infer_effocr.py:286-291: int(round(.)) (banker's) on all four coordinates, then double clipping."""
+    x0, y0, x1, y1 = map(int, map(round, (float(v) for v in bbox[:4])))
+    if double_clipped:
+        if vertical:
+            x0, x1 = 0, im_width
+        else:
+            y0, y1 = 0, im_height
+    return x0, y0, x1, y1
+
+
+class EffOCRPipeline:
+    """localizer (EffLocalizer) + recognizer (RecognizerPipeline) + candidate chars."""
+
+    def __init__(self, localizer: EffLocalizer, recognizer: RecognizerPipeline, candidate_chars, lang: str = "en",
+                 vertical: bool = False, knn: int = 1, anchor_margin=None, blacklist=None):
+        self.localizer = localizer
+        self.recognizer = recognizer
+        self.candidate_chars = list(candidate_chars)
+        self.lang = lang
+        self.vertical = vertical
+        self.knn = knn
+        self.anchor_margin = anchor_margin
+        if blacklist:  # infer_effocr.py:209-212
+            ids = np.array([self.candidate_chars.index(c) for c in blacklist])
+            self.recognizer.index.remove_ids(ids)
+            self.candidate_chars = [c for c in self.candidate_chars if c not in blacklist]
+
+    # -- phase 1: localize a batch of RGB u8 line images
+    def localize(self, images_rgb):
+        shape = self.localizer._input_shape
+        lb = [EffLocalizer.preprocess_bgr(np.ascontiguousarray(im[:, :, ::-1]), shape) for im in images_rgb]
+        x = torch.from_numpy(np.concatenate(lb, 0)).cuda(non_blocking=True)
+        out, cnt = self.localizer.run_device(x)
+        out, cnt = out.cpu(), cnt.cpu().tolist()
+        return [out[i, :cnt[i]] for i in range(len(images_rgb))]
+
+    # -- host logic between the two GPU phases (reference semantics, ONNX path)
+    def _boxes_for_line(self, result, im_h, im_w):
+        bboxes, labels = result[:, :4], result[:, -1]
+        word_end_idx = []
+        if self.lang == "en":
+            char_b, word_b = bboxes[labels == 0], bboxes[labels == 1]
+            if len(char_b) != 0:
+                char_b, word_end_idx = textproc.en_preprocess(char_b, word_b)
+        else:
+            char_b = bboxes[labels == 0]
+            if len(char_b) != 0:
+                char_b = textproc.jp_preprocess(char_b, vertical=self.vertical)
+        rects = [crop_rect_onnx_path(b, im_h, im_w, self.vertical) for b in char_b]
+        heights = [b[3] - b[1] for b in char_b]
+        bottoms = [b[3] for b in char_b]
+        return list(char_b), word_end_idx, rects, heights, bottoms
+
+    def infer_lines(self, images_rgb):
+        """images_rgb: list of u8 [H, W, 3] arrays -> list of dicts (text, nns, char_boxes, word_end_idx)."""
+        if len(images_rgb) == 0:
+            return []
+        dets = self.localize(images_rgb)
+        per_line, all_rects = [], []
+        for li, (im, det) in enumerate(zip(images_rgb, dets)):
+            h, w = im.shape[:2]
+            char_b, wei, rects, heights, bottoms = self._boxes_for_line(det, h, w)
+            per_line.append((char_b, wei, heights, bottoms, len(rects)))
+            all_rects += [(li,) + r for r in rects]
+        results = []
+        if all_rects:
+            packed = PackedCrops(images_rgb, all_rects)
+            dist, idx = self.recognizer.recognize_packed(packed, self.knn)
+        pos = 0
+        for (char_b, wei, heights, bottoms, n) in per_line:
+            if n == 0:
+                results.append({"text": None, "nns": [], "char_boxes": [], "word_end_idx": []})
+                continue
+            rows = idx[pos:pos + n]
+            pos += n
+            nearest = [[self.candidate_chars[j] for j in row if j >= 0] for row in rows.tolist()]
+            nns = ["".join(c).strip() for c in nearest]
+            text = "".join(x[0] for x in nearest).strip()
+            if self.lang == "en":
+                # the ONNX driver passes the un-stripped first-NN string's characters; lengths must agree (:94)
+                first = [x[0] for x in nearest]
+                text = textproc.en_postprocess(first, wei, heights, bottoms, anchor_margin=self.anchor_margin)
+            results.append({"text": text, "nns": nns, "char_boxes": [b.tolist() for b in char_b], "word_end_idx": wei})
+        return results
+
+
+def run_effocr(images_rgb, pipeline: EffOCRPipeline, batch_lines: int = 64, keys=None):
+    """-> {key: text}; `keys` default to the line index.  Mirrors run_effocr's return (inference_results)."""
+    keys = list(range(len(images_rgb))) if keys is None else list(keys)
+    out = {}
+    for i0 in range(0, len(images_rgb), batch_lines):
+        res = pipeline.infer_lines(images_rgb[i0:i0 + batch_lines])
+        for k, r in zip(keys[i0:i0 + batch_lines], res):
+            out[k] = r["text"]
+    return out
