@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-random", action="store_true",
+                    help="profiling runs: random unit-norm prototypes instead of embedding rendered glyphs")
     return ap.parse_args()
 
 
@@ -248,7 +250,10 @@ def main():
 
     boot = RecognizerPipeline(sd, torch.zeros(1, D), max_batch=B)
     index_vectors = torch.empty((args.index, D), device="cuda", dtype=torch.float32)
-    if rank == 0:
+    if rank == 0 and args.index_random:
+        g = torch.Generator().manual_seed(1)
+        index_vectors.copy_(torch.nn.functional.normalize(torch.randn(args.index, D, generator=g), dim=1))
+    elif rank == 0:
         glyphs = synth.glyph_images(args.index)
         for i0 in range(0, args.index, B):
             chunk = PackedCrops(glyphs[i0:i0 + B])

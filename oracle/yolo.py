@@ -189,23 +189,30 @@ def load_localizer_img_from_array(im_bgr: np.ndarray, input_shape=(640, 640)) ->
 
 # ------------------------------------------------------------------ NMS (localizer_engine.py:171-277)
 def nms_greedy(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float) -> torch.Tensor:
-    """torchvision.ops.nms semantics: visit boxes by descending score (ties: lower index first), keep a
-    box unless its IoU with an already kept box is strictly greater than iou_thres."""
-    order = torch.sort(scores, descending=True, stable=True).indices.tolist()
-    b = boxes.double()
-    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    """torchvision.ops.nms semantics (its CPU kernel, fp32 op for op): visit boxes by descending score (ties:
+    lower index first), keep a box unless its IoU with an already kept box is strictly greater than iou_thres;
+    IoU = inter / (area_i + area_j - inter) with inter = max(0, xx2 - xx1) * max(0, yy2 - yy1)."""
+    order = torch.sort(scores, descending=True, stable=True).indices.numpy()
+    b = boxes.numpy().astype(np.float32)[order]
+    x1, y1, x2, y2 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    areas = ((x2 - x1) * (y2 - y1)).astype(np.float32)
+    n = len(order)
+    suppressed = np.zeros(n, dtype=bool)
     keep = []
-    for i in order:
-        ok = True
-        for j in keep:
-            xx1, yy1 = max(b[i, 0], b[j, 0]), max(b[i, 1], b[j, 1])
-            xx2, yy2 = min(b[i, 2], b[j, 2]), min(b[i, 3], b[j, 3])
-            inter = max(xx2 - xx1, 0.0) * max(yy2 - yy1, 0.0)
-            if inter / (area[i] + area[j] - inter) > iou_thres:
-                ok = False
-                break
-        if ok:
-            keep.append(i)
+    thr = np.float32(iou_thres)
+    for i in range(n):
+        if suppressed[i]:
+            continue
+        keep.append(int(order[i]))
+        xx1 = np.maximum(x1[i], x1[i + 1:])
+        yy1 = np.maximum(y1[i], y1[i + 1:])
+        xx2 = np.minimum(x2[i], x2[i + 1:])
+        yy2 = np.minimum(y2[i], y2[i + 1:])
+        w = np.maximum(np.float32(0), (xx2 - xx1).astype(np.float32))
+        h = np.maximum(np.float32(0), (yy2 - yy1).astype(np.float32))
+        inter = (w * h).astype(np.float32)
+        ovr = (inter / ((areas[i] + areas[i + 1:]).astype(np.float32) - inter).astype(np.float32)).astype(np.float32)
+        suppressed[i + 1:] |= ovr > thr
     return torch.tensor(keep, dtype=torch.int64)
 
 

@@ -62,3 +62,28 @@ def test_product_fails_without_cuda():
     enc = AutoEncoderFactory("timm", "vit_tiny_patch16_224")(device="cpu")
     with pytest.raises(_lib.EffocrError):
         enc(torch.zeros(1, 3, 224, 224))
+
+
+def test_dropin_registers_reference_module_names():
+    import sys
+    saved = {k: sys.modules.get(k) for k in ("faiss", "models.encoders", "onnx_engines.localizer_engine")}
+    try:
+        from effocr_b200 import dropin
+        names = dropin.install(force=True)
+        assert "faiss" in names
+        import faiss
+        from models.encoders import AutoEncoderFactory
+        from onnx_engines.localizer_engine import EffLocalizer
+        from pytorch_metric_learning.utils.inference import FaissKNN, InferenceModel
+        assert callable(faiss.IndexFlatIP) and callable(AutoEncoderFactory) and hasattr(EffLocalizer, "non_max_suppression")
+        assert FaissKNN(reset_before=False, reset_after=False).index is None
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+        for k in ("models", "onnx_engines", "onnx_engines.recognizer_engine", "pytorch_metric_learning",
+                  "pytorch_metric_learning.utils", "pytorch_metric_learning.utils.inference", "nltk", "nltk.metrics",
+                  "nltk.metrics.distance"):
+            sys.modules.pop(k, None)
