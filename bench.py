@@ -68,7 +68,7 @@ def encoder_state(seed: int = 0):
 
 # ------------------------------------------------------------------------------- clocks sampler
 class ClockSampler(threading.Thread):
-    def __init__(self, device_index: int, period_s: float = 0.1):
+    def __init__(self, device_index: int, period_s: float = 0.01):
         super().__init__(daemon=True)
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop_evt = threading.Event()
