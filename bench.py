@@ -224,6 +224,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -50,7 +50,7 @@ SIGNATURES = {
     "effocr_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_int,
                                  c_void_p]),
-    "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "effocr_yolo_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "effocr_yolo_destroy": (None, [c_void_p]),
     "effocr_yolo_num_predictions": (c_int, [c_int, c_int]),

@@ -46,11 +46,6 @@ struct GemmCfg {
 };
 
 // ------------------------------------------------------------------ epilogue helpers
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 __device__ __forceinline__ float gelu_erf(float x) {
   // exact-erf GELU (timm nn.GELU default), x * Phi(x), written as
   //     gelu(x) = relu(x) - |x| * Phi(-|x|),     Phi(-u) = 2^P(u),  u = min(|x|, 6)

@@ -8,6 +8,7 @@
 
 #include "../../include/effocr_b200.h"
 #include "gemm.h"
+#include "attention_sm100.cuh"
 #include "vit_kernels.cuh"
 
 namespace effocr {
@@ -82,17 +83,33 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
   return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s) {
+// impl 0: tcgen05 kernel (attention_sm100.cuh); impl 1: first-generation mma.sync kernel (kept as an A/B reference)
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
-  static bool attr = false;
-  if (!attr) {
-    EFFOCR_CUDA(cudaFuncSetAttribute(attention_197x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
-    attr = true;
-  }
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  {
+  if (impl == 1) {
+    static bool attr = false;
+    if (!attr) {
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_197x64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+      attr = true;
+    }
     KernelScope ks(PROF_ATTENTION, s);
     attention_197x64_kernel<<<batch * H, kAttnThreads, kAttnSmemBytes, s>>>(qkv, out, T, H, scale_log2e);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      attr = true;
+    }
+    const long long rows = static_cast<long long>(batch) * T;
+    const int D = H * 64;
+    CUtensorMap tq, tkv;
+    EFFOCR_TRY(make_tmap_f16_2d(&tq, qkv, rows, 3 * D, 3 * D, 128));
+    EFFOCR_TRY(make_tmap_f16_2d(&tkv, qkv, rows, 3 * D, 3 * D, kAtN));
+    const int pairs = batch * H;
+    const int grid = pairs < sm_count() ? pairs : sm_count();
+    KernelScope ks(PROF_ATTENTION, s);
+    attention_tc_kernel<<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
@@ -249,9 +266,10 @@ extern "C" int effocr_layernorm(const float* d_x, long long ldx, const float* d_
                  : layernorm_f16(d_x, ldx, d_gamma, d_beta, reinterpret_cast<__half*>(d_out), ldo, rows, dim, eps, s);
 }
 
-extern "C" int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, void* stream) {
+extern "C" int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, int impl,
+                                    void* stream) {
   EFFOCR_TRY(require_sm100());
   if (batch <= 0) return EFFOCR_OK;
   return attention_f16(reinterpret_cast<const __half*>(d_qkv), reinterpret_cast<__half*>(d_out), batch, tokens, heads,
-                       reinterpret_cast<cudaStream_t>(stream));
+                       reinterpret_cast<cudaStream_t>(stream), impl);
 }

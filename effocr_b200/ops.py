@@ -61,12 +61,12 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def attention(qkv: torch.Tensor, batch: int, heads: int) -> torch.Tensor:
+def attention(qkv: torch.Tensor, batch: int, heads: int, impl: int = 0) -> torch.Tensor:
     lib = _lib.load()
     qkv = _cuda(qkv, torch.float16, "qkv")
     tokens = qkv.shape[0] // batch
     out = torch.empty((qkv.shape[0], heads * 64), device=qkv.device, dtype=torch.float16)
-    _lib.check(lib.effocr_attention_f16(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, _lib.stream_ptr()),
+    _lib.check(lib.effocr_attention_f16(qkv.data_ptr(), out.data_ptr(), batch, tokens, heads, impl, _lib.stream_ptr()),
                "effocr_attention_f16")
     return out
 

@@ -119,8 +119,10 @@ EFFOCR_API int effocr_vit_forward(effocr_vit_t h, const void* d_input, int input
 /* building blocks of the encoder, exported for the parity tests */
 EFFOCR_API int effocr_layernorm(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta,
                                 void* d_out, long long ldo, int rows, int dim, float eps, int out_f32, void* stream);
-/* qkv fp16 [B*197, 3*H*64] (rows [q|k|v], each [H,64]) -> out fp16 [B*197, H*64] */
-EFFOCR_API int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, void* stream);
+/* qkv fp16 [B*197, 3*H*64] (rows [q|k|v], each [H,64]) -> out fp16 [B*197, H*64].
+ * impl 0: tcgen05 kernel (S and O in TMEM, V consumed in place as an MN-major operand); impl 1: mma.sync kernel. */
+EFFOCR_API int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, int impl,
+                                    void* stream);
 
 /* ---- localizer: YOLOv5s forward (ultralytics yolov5s.yaml, nc classes) ---------------------------
  * Replaces the onnxruntime session behind EffLocalizer.run (onnx_engines/localizer_engine.py:25-29,49-55).

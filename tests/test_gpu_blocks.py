@@ -82,13 +82,14 @@ def test_layernorm(dim, f32):
     assert _rel(out, ref) < (2e-6 if f32 else 4e-4)
 
 
-@pytest.mark.parametrize("batch,heads", [(1, 3), (5, 6), (64, 6)])
-def test_attention(batch, heads):
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("batch,heads", [(1, 3), (5, 6), (64, 6), (200, 3)])
+def test_attention(batch, heads, impl):
     from effocr_b200 import ops
     torch.manual_seed(0)
     T, D = 197, heads * 64
     qkv = (torch.randn(batch * T, 3 * D, device="cuda") * 1.5).half()
-    out = ops.attention(qkv, batch, heads)
+    out = ops.attention(qkv, batch, heads, impl=impl)
     q, k, v = qkv.float().reshape(batch, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     att = (q @ k.transpose(-2, -1) * 0.125).softmax(-1)
     ref = (att @ v).transpose(1, 2).reshape(batch * T, D)
