@@ -1,18 +1,20 @@
 // Fused multi-head attention for the fixed ViT/16 @ 224 sequence (197 tokens, head dim 64) on tcgen05.
 //
-// One persistent CTA per SM walks (image, head) pairs.  For each pair and each 128-row query tile:
+// One persistent CTA per SM walks (image, head) pairs; the two 128-row query tiles of a pair are processed
+// concurrently by two groups of four softmax warps:
 //
-//   S = Q K^T      tcgen05.mma  M=128, N=208 (197 keys padded to a multiple of 16), K=64; fp32 S in TMEM
-//   softmax        4 warps, one thread per query row: two passes over the S row with tcgen05.ld
-//                  (row max, then exp2 / row sum), P written as fp16 into a 128-byte-swizzled smem tile
-//   O = P V        tcgen05.mma  M=128, N=64, K=208; A = P (K-major, smem), B = V used in place as an
-//                  MN-major operand (V is [key][dim] in memory: no transpose pass), fp32 O in TMEM
-//   epilogue       O / rowsum -> fp16 -> global, rows < 197 only
+//   S_g = Q_g K^T   tcgen05.mma  M=128, N=208 (197 keys padded to a multiple of 16), K=64; fp32 S in TMEM
+//   softmax         one thread per query row: two passes over the S row with tcgen05.ld (row max, then
+//                   exp2 / row sum, next chunk prefetched), P written as fp16 into swizzled smem
+//   O_g = P_g V     tcgen05.mma  M=128, N=64, K=208; A = P (K-major smem: three 64-key SWIZZLE_128B chunks +
+//                   one 16-key SWIZZLE_32B tail), B = V used in place as an MN-major operand (V is
+//                   [key][dim] in memory: no transpose pass); fp32 O in TMEM, aliased onto S_g's columns
+//   epilogue        O / rowsum -> fp16 -> global, rows < 197 only
 //
-// Q, K, V tiles come straight out of the fused QKV GEMM's output ([B*197, 3*H*64] fp16) by TMA; K/V of the
-// next pair and the next Q tile are prefetched while the current tile is processed.  Keys 197..207 of a K/V
-// box belong to the next image (or are zero-filled at the end of the tensor); they are masked to -inf before
-// the softmax, so P is exactly 0 there.
+// Q, K, V tiles come straight out of the fused QKV GEMM's output ([B*197, 3*H*64] fp16) by TMA; K of the next
+// pair is prefetched (double buffer), V is single-buffered (its reload hides behind the next pair's S + softmax).
+// Keys 197..207 of a K/V box belong to the next image (or are zero-filled at the end of the tensor); they are
+// masked before the softmax, so P is exactly 0 there.
 //
 // Replaces the attention inside timm's Block.forward reached from /root/reference/models/encoders.py:62-64.
 #pragma once
@@ -20,14 +22,16 @@
 
 namespace effocr {
 
-constexpr int kAtT = 197;        // tokens
-constexpr int kAtN = 208;        // keys padded to a multiple of 16 (UMMA N granularity at M=128)
-constexpr int kAtQBytes = 128 * 128;     // 128 rows x 64 fp16
-constexpr int kAtKVBytes = kAtN * 128;   // 208 rows x 64 fp16
-constexpr int kAtPBytes = 4 * 128 * 128; // 4 chunks of 64 keys x 128 rows
-constexpr int kAtThreads = 256;
-constexpr int kAtSmemBytes = 2 * kAtQBytes + 4 * kAtKVBytes + kAtPBytes + 256 + 1024;
-constexpr uint32_t kAtTmemS = 0, kAtTmemO = 256;
+constexpr int kAtT = 197;                 // tokens
+constexpr int kAtN = 208;                 // keys padded to a multiple of 16 (UMMA N granularity at M=128)
+constexpr int kAtQBytes = 128 * 128;      // 128 rows x 64 fp16
+constexpr int kAtKVBytes = kAtN * 128;    // 208 rows x 64 fp16
+constexpr int kAtPMain = 3 * 128 * 128;   // keys 0..191: three SWIZZLE_128B chunks
+constexpr int kAtPTail = 128 * 32;        // keys 192..207: one SWIZZLE_32B chunk
+constexpr int kAtPBytes = kAtPMain + kAtPTail;
+constexpr int kAtThreads = 384;
+constexpr int kAtSmemBytes = 2 * kAtQBytes + 3 * kAtKVBytes + 2 * kAtPBytes + 256 + 1024;
+constexpr uint32_t kAtTmemRegion = 256;   // columns per query-tile group (S: 208, O aliases the first 64)
 
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -50,6 +54,16 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) 
   d |= static_cast<uint64_t>(2) << 61;              // SWIZZLE_128B
   return d;
 }
+// K-major operand tile with 32-byte rows (16 fp16 = one UMMA K step), SWIZZLE_32B: 8-row atoms of 256 B.
+__device__ __forceinline__ uint64_t make_sw32_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;       // SBO: 8 rows x 32 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;              // SWIZZLE_32B
+  return d;
+}
 // kind::f16, fp16 A (K-major) x fp16 B (MN-major), fp32 accumulate
 __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {
   return make_idesc_f16(M, N) | (1u << 16);
@@ -60,20 +74,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
                     __half* __restrict__ out, int batch, int H, float scale_log2e) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem;                              // 2 x 16 KB
-  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // 2 x 26 KB
-  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 2 x 26 KB
-  uint8_t* smem_p = smem_v + 2 * kAtKVBytes;           // 64 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + kAtPBytes);
-  uint64_t* q_full = bars;        // [2]
-  uint64_t* q_empty = bars + 2;   // [2]
-  uint64_t* kv_full = bars + 4;   // [2]
-  uint64_t* kv_empty = bars + 6;  // [2]
-  uint64_t* s_full = bars + 8;
-  uint64_t* p_full = bars + 9;
-  uint64_t* o_full = bars + 10;
-  uint64_t* t_free = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
+  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // [2 pair parities] x 26 KB
+  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 26 KB
+  uint8_t* smem_p = smem_v + kAtKVBytes;               // [2 groups] x 52 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;     // [2]
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_empty = bars + 9;
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* o_full = bars + 14;    // [2]
+  uint64_t* t_free = bars + 16;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -88,13 +104,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 4);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
-    mbar_init(t_free, 4);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -110,21 +128,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     // ---------------- TMA producer
     if (elect_one_sync()) {
       int it = 0;  // pair counter of this CTA
-      int qt = 0;  // query-tile counter of this CTA
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
         const int b = bh / H, h = bh % H;
         const int row0 = b * kAtT;
         const int s = it & 1;
-        mbar_wait(&kv_empty[s], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * kAtKVBytes);
-        tma_load_2d(&tma_kv, &kv_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
-        tma_load_2d(&tma_kv, &kv_full[s], smem_v + s * kAtKVBytes, 2 * D + h * 64, row0);
-        for (int m = 0; m < 2; ++m, ++qt) {
-          const int qs = qt & 1;
-          mbar_wait(&q_empty[qs], ((qt >> 1) & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[qs], kAtQBytes);
-          tma_load_2d(&tma_q, &q_full[qs], smem_q + qs * kAtQBytes, h * 64, row0 + m * 128);
+        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
+        mbar_wait(&k_empty[s], par2 ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], kAtKVBytes);
+        tma_load_2d(&tma_kv, &k_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_empty[g], par ^ 1);
+          mbar_arrive_expect_tx(&q_full[g], kAtQBytes);
+          tma_load_2d(&tma_q, &q_full[g], smem_q + g * kAtQBytes, h * 64, row0 + g * 128);
         }
+        mbar_wait(v_empty, par ^ 1);
+        mbar_arrive_expect_tx(v_full, kAtKVBytes);
+        tma_load_2d(&tma_kv, v_full, smem_v, 2 * D + h * 64, row0);
       }
     }
   } else if (warp_idx == 1) {
@@ -132,78 +151,93 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
       constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
-      int it = 0, qt = 0;
+      int it = 0;
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
         const int s = it & 1;
-        mbar_wait(&kv_full[s], (it >> 1) & 1);
-        for (int m = 0; m < 2; ++m, ++qt) {
-          const int qs = qt & 1;
-          mbar_wait(&q_full[qs], (qt >> 1) & 1);
-          mbar_wait(t_free, (qt & 1) ^ 1);  // S/O columns drained by the previous tile's epilogue
+        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
+        mbar_wait(&k_full[s], par2);
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem_k + s * kAtKVBytes));
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_full[g], par);
+          mbar_wait(&t_free[g], par ^ 1);  // region g (S/O columns) drained by the previous pair's epilogue
           tcgen05_fence_after();
-          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + qs * kAtQBytes));
-          const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem_k + s * kAtKVBytes));
+          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + g * kAtQBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kAtTmemS, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(&q_empty[qs]);
-          umma_commit(s_full);
-          // P V once the softmax warps have written P
-          mbar_wait(p_full, qt & 1);
-          tcgen05_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < kAtN / 16; ++ks) {
-            const uint64_t dp = make_sw128_kmajor_desc(smem_u32(smem_p + (ks >> 2) * kAtQBytes)) + 2 * (ks & 3);
-            const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem_v + s * kAtKVBytes + ks * 2048));
-            umma_f16(tmem_base + kAtTmemO, dp, dv, idesc_o, ks ? 1u : 0u);
-          }
-          if (m == 1) umma_commit(&kv_empty[s]);
-          umma_commit(o_full);
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(&q_empty[g]);
+          umma_commit(&s_full[g]);
         }
+        umma_commit(&k_empty[s]);
+        mbar_wait(v_full, par);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], par);  // all four warps of the group have read S_g and written P_g
+          tcgen05_fence_after();
+          const uint32_t pbase = smem_u32(smem_p + g * kAtPBytes);
+#pragma unroll
+          for (int ks = 0; ks < 12; ++ks) {
+            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+            const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem_v + ks * 2048));
+            umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+          }
+          umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
+                   make_sw128_mnmajor_desc(smem_u32(smem_v + 12 * 2048)), idesc_o, 1u);
+          umma_commit(&o_full[g]);
+        }
+        umma_commit(v_empty);
       }
     }
   } else if (warp_idx >= 4) {
-    // ---------------- softmax + epilogue: thread = query row
+    // ---------------- softmax + epilogue: group g = query tile, thread = query row
+    const int g = (warp_idx - 4) >> 2;
     const int q = warp_idx & 3;
     const int r = q * 32 + lane;  // row inside the 128-row tile
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    int qt = 0;
-    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x) {
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
+    uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
+    uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    int it = 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
       const int b = bh / H, h = bh % H;
-      for (int m = 0; m < 2; ++m, ++qt) {
-        mbar_wait(s_full, qt & 1);
-        tcgen05_fence_after();
-        // pass 1: row maximum over the 197 valid keys
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(trow + kAtTmemS + c * 32, v);
-          tmem_ld_wait();
+      const uint32_t par = it & 1;
+      mbar_wait(&s_full[g], par);
+      tcgen05_fence_after();
+      // pass 1: row maximum over the 197 valid keys (chunk c+1 in flight while chunk c is reduced)
+      float mx = -INFINITY;
+      {
+        uint32_t v[2][32];
+        uint32_t vt[16];
+        tmem_ld_32x32b_x32(trow, v[0]);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(trow + kAtTmemS + 192, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 5; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));  // keys 192..196
-        }
-        const float moff = mx * scale_log2e;
-        // pass 2: p = 2^(s * scale - max * scale), row sum, P -> smem (fp16, 128-byte swizzle, K-major)
-        float sum = 0.f;
-#pragma unroll 1
         for (int c = 0; c < 6; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(trow + kAtTmemS + c * 32, v);
           tmem_ld_wait();
+          if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+          else tmem_ld_32x32b_x16(trow + 192, vt);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c & 1][i]));
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 5; ++i) mx = fmaxf(mx, __uint_as_float(vt[i]));  // keys 192..196
+      }
+      const float moff = mx * scale_log2e;
+      // pass 2: p = 2^(s * scale - max * scale), row sum, P -> smem (fp16, K-major, swizzled)
+      float sum = 0.f;
+      {
+        uint32_t v[2][32];
+        uint32_t vt[16];
+        tmem_ld_32x32b_x32(trow, v[0]);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+          else tmem_ld_32x32b_x16(trow + 192, vt);
           float p[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            p[i] = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2e, -moff));
+            p[i] = ex2_approx(fmaf(__uint_as_float(v[c & 1][i]), scale_log2e, -moff));
             sum += p[i];
           }
-          uint8_t* chunk = smem_p + (c >> 1) * kAtQBytes + r * 128;
+          uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
@@ -214,63 +248,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
             *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk;
           }
         }
-        {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(trow + kAtTmemS + 192, v);
-          tmem_ld_wait();
-          float p[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            p[i] = (i < 5) ? ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2e, -moff)) : 0.f;  // keys >= 197 masked
-            sum += p[i];
-          }
-          uint8_t* chunk = smem_p + 3 * kAtQBytes + r * 128;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 pk;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(p[8 * j + 2 * t], p[8 * j + 2 * t + 1]);
-            *reinterpret_cast<uint4*>(chunk + ((j ^ (r & 7)) << 4)) = pk;
-          }
-        }
-        // S fully read and P written: make the generic-proxy writes visible to the MMA (async proxy), then signal
-        tcgen05_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        // epilogue: O / sum -> fp16 -> global
-        mbar_wait(o_full, qt & 1);
-        tcgen05_fence_after();
-        const float inv = 1.0f / sum;
-        const int tok = m * 128 + r;
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32b_x32(trow + kAtTmemO, o0);
-        tmem_ld_32x32b_x32(trow + kAtTmemO + 32, o1);
         tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(t_free);
-        if (tok < kAtT) {
-          __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
+        float p[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
+        for (int i = 0; i < 16; ++i) {
+          p[i] = (i < 5) ? ex2_approx(fmaf(__uint_as_float(vt[i]), scale_log2e, -moff)) : 0.f;  // keys >= 197 masked
+          sum += p[i];
+        }
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              ph[t] = __floats2half2_rn(__uint_as_float(o0[8 * j + 2 * t]) * inv, __uint_as_float(o0[8 * j + 2 * t + 1]) * inv);
-            *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
-          }
+        for (int j = 0; j < 2; ++j) {
+          uint4 pk;
+          __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 pk;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
+          for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(p[8 * j + 2 * t], p[8 * j + 2 * t + 1]);
+          *reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4)) = pk;  // SWIZZLE_32B: bit 4 ^= bit 7
+        }
+      }
+      // S fully read and P written: make the generic-proxy writes visible to the MMA (async proxy), then signal
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      // epilogue: O / sum -> fp16 -> global
+      mbar_wait(&o_full[g], par);
+      tcgen05_fence_after();
+      const float inv = 1.0f / sum;
+      const int tok = g * 128 + r;
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(trow, o0);
+      tmem_ld_32x32b_x32(trow + 32, o1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[g]);
+      if (tok < kAtT) {
+        __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              ph[t] = __floats2half2_rn(__uint_as_float(o1[8 * j + 2 * t]) * inv, __uint_as_float(o1[8 * j + 2 * t + 1]) * inv);
-            *reinterpret_cast<uint4*>(dst + 32 + 8 * j) = pk;
-          }
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            ph[t] = __floats2half2_rn(__uint_as_float(o0[8 * j + 2 * t]) * inv, __uint_as_float(o0[8 * j + 2 * t + 1]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            ph[t] = __floats2half2_rn(__uint_as_float(o1[8 * j + 2 * t]) * inv, __uint_as_float(o1[8 * j + 2 * t + 1]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + 8 * j) = pk;
         }
       }
     }

@@ -52,6 +52,9 @@ __device__ __forceinline__ void numpy_slice(int start, int stop, int n, int* lo,
   *len = stop > start ? stop - start : 0;
 }
 
+constexpr int kCropMaxStage = 3072;  // staged source pixels (float4 each) per block: 48 KB
+constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4;
+
 template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16)
 __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restrict__ pixels,
                                                           const effocr_image_desc* __restrict__ images,
@@ -74,7 +77,71 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[c][k] = 0.f;
 
+  // ---- fast path (block-uniform): the 8 output rows of this block read a small band of source rows; stage it in
+  // shared memory as float RGB once (each source pixel feeds ~12 outputs when a 64-px crop is blown up to 224)
+  // together with the horizontal tap table, so the inner loop is LDS.128 + FMA only.
+  extern __shared__ __align__(16) uint8_t crop_smem[];
+  float4* s_src = reinterpret_cast<float4*>(crop_smem);                         // [kCropMaxStage]
+  float4* s_xw = s_src + kCropMaxStage;                                         // [224] horizontal weights (<= 4 taps)
+  int* s_xmn = reinterpret_cast<int*>(s_xw + OUT);                              // [224] first horizontal tap
+  bool fast = false;
   if (!empty) {
+    const int S = h > w ? h : w;
+    const float scale = static_cast<float>(S) / static_cast<float>(OUT);
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float invscale = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const AxisTaps tf = make_taps(blockIdx.x * 8, scale, support, invscale, S);
+    const AxisTaps tl = make_taps(blockIdx.x * 8 + 7, scale, support, invscale, S);
+    const int r0 = tf.mn, nrows = tl.mn + tl.sz - tf.mn;
+    fast = scale <= 1.5f && nrows > 0 && nrows * S <= kCropMaxStage;
+    if (fast) {
+      const uint8_t* src = pixels + im.offset + static_cast<long long>(y_lo) * im.pitch + static_cast<long long>(x_lo) * 3;
+      for (int idx = threadIdx.x; idx < nrows * S; idx += blockDim.x) {
+        const int rr = idx / S, xx = idx - rr * S;
+        const int y = r0 + rr;
+        float4 px = make_float4(1.f, 1.f, 1.f, 0.f);  // white pad right / bottom
+        if (y < h && xx < w) {
+          const uint8_t* p = src + static_cast<long long>(y) * im.pitch + xx * 3;
+          px.x = static_cast<float>(__ldg(p)) * (1.0f / 255.0f);
+          px.y = static_cast<float>(__ldg(p + 1)) * (1.0f / 255.0f);
+          px.z = static_cast<float>(__ldg(p + 2)) * (1.0f / 255.0f);
+        }
+        s_src[idx] = px;
+      }
+      for (int j = threadIdx.x; j < OUT; j += blockDim.x) {
+        const AxisTaps tx = make_taps(j, scale, support, invscale, S);
+        s_xmn[j] = tx.mn;
+        s_xw[j] = make_float4(tx.sz > 0 ? tap_weight(tx, 0, invscale) : 0.f, tx.sz > 1 ? tap_weight(tx, 1, invscale) : 0.f,
+                              tx.sz > 2 ? tap_weight(tx, 2, invscale) : 0.f, tx.sz > 3 ? tap_weight(tx, 3, invscale) : 0.f);
+      }
+      __syncthreads();
+      const AxisTaps ty = make_taps(i, scale, support, invscale, S);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int xmn = s_xmn[j0 + k];
+        const float4 xw = s_xw[j0 + k];
+        const float wxs[4] = {xw.x, xw.y, xw.z, xw.w};
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (int yy = 0; yy < ty.sz; ++yy) {
+          const float wy = tap_weight(ty, yy, invscale);
+          const float4* rowp = s_src + (ty.mn - r0 + yy) * S;
+          float rr = 0.f, gg = 0.f, bb = 0.f;
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx) {
+            const int x = xmn + xx < S ? xmn + xx : S - 1;  // weights beyond the tap count are zero
+            const float4 px = rowp[x];
+            rr = fmaf(wxs[xx], px.x, rr); gg = fmaf(wxs[xx], px.y, gg); bb = fmaf(wxs[xx], px.z, bb);
+          }
+          r = fmaf(wy, rr, r); g = fmaf(wy, gg, g); b = fmaf(wy, bb, b);
+        }
+        acc[0][k] = (r - 0.485f) / 0.229f;
+        acc[1][k] = (g - 0.456f) / 0.224f;
+        acc[2][k] = (b - 0.406f) / 0.225f;
+      }
+    }
+  }
+
+  if (!empty && !fast) {
     const int S = h > w ? h : w;
     const float scale = static_cast<float>(S) / static_cast<float>(OUT);
     const float support = scale >= 1.0f ? scale : 1.0f;
@@ -146,11 +213,18 @@ extern "C" int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
   if (n_boxes > 65535) return fail(EFFOCR_ERR_INVALID, "crop_resize: at most 65535 boxes per call");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(28, n_boxes);
+  static bool attr = false;
+  if (!attr) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
+    EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
+    EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
+    attr = true;
+  }
   KernelScope ks(PROF_CROP, s);
   switch (layout) {
-    case EFFOCR_CROP_NCHW_F16: crop_resize_kernel<0><<<grid, 224, 0, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
-    case EFFOCR_CROP_NCHW_F32: crop_resize_kernel<1><<<grid, 224, 0, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
-    case EFFOCR_CROP_PATCH_F16: crop_resize_kernel<2><<<grid, 224, 0, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
+    case EFFOCR_CROP_NCHW_F16: crop_resize_kernel<0><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
+    case EFFOCR_CROP_NCHW_F32: crop_resize_kernel<1><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
+    case EFFOCR_CROP_PATCH_F16: crop_resize_kernel<2><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
     default: return fail(EFFOCR_ERR_INVALID, "crop_resize: unknown layout");
   }
   EFFOCR_CUDA(cudaGetLastError());
