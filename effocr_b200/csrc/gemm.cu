@@ -122,6 +122,40 @@ static int launch_astat(const GemmArgs& a, cudaStream_t stream) {
   return EFFOCR_OK;
 }
 
+// CTA-pair (cta_group::2) schedule: 256 x BN tiles, BN in {192, 256}
+template <int BN, int ACT, bool F32, bool RED>
+static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmPairCfg<BN, F32>;
+  CUtensorMap ta, tb, tc;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN / 2));
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, 32, 32, F32 ? 128 : 64));
+  auto kern = gemm_tn_pair_kernel<BN, ACT, F32, RED>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((a.M + 2 * kBlockM - 1) / (2 * kBlockM)) * ((a.N + BN - 1) / BN);
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  EpiTmaParams ep;
+  ep.bias = a.bias;
+  ep.gamma = a.gamma;
+  {
+    KernelScope ks(a.prof_tag, stream);
+    kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+static bool use_pair(int bn, const GemmArgs& a) {
+  if (a.epilogue != 3) return false;  // opt-in while the schedule is being validated
+  const int num_m = (a.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  return (bn == 192 || bn == 256) && num_m * ((a.N + bn - 1) / bn) >= sm_count() / 2;
+}
+
 static bool use_astat(int bn, const GemmArgs& a) {
   if (a.epilogue == 2) return false;
   const int num_n = (a.N + bn - 1) / bn;
@@ -132,6 +166,10 @@ static bool use_astat(int bn, const GemmArgs& a) {
 
 template <int ACT, bool F32, bool RED>
 static int launch_tma_bn(int bn, const GemmArgs& a, cudaStream_t stream) {
+  if (use_pair(bn, a)) {
+    if (bn == 192) return launch_pair<192, ACT, F32, RED>(a, stream);
+    return launch_pair<256, ACT, F32, RED>(a, stream);
+  }
   if (use_astat(bn, a)) {
     if (bn == 192) return launch_astat<192, ACT, F32, RED>(a, stream);
     return launch_astat<256, ACT, F32, RED>(a, stream);
@@ -147,7 +185,7 @@ static int launch_tma_bn(int bn, const GemmArgs& a, cudaStream_t stream) {
 
 // Returns -1 when the TMA epilogue does not apply (caller falls back to the direct-store epilogue).
 static int try_gemm_tma(int bn, const GemmArgs& a, cudaStream_t stream) {
-  if (a.pos || a.epilogue == 1) return -1;
+  if (a.pos || a.epilogue == 1) return -1;  // epilogue: 0 auto, 1 direct store, 2 TMA/no A-stat, 3 CTA pair
   const bool inplace = a.resid != nullptr && a.resid == a.out && a.ldr == a.ldo;
   if (a.resid && !inplace) return -1;
   if (a.out_f32) {

@@ -41,6 +41,58 @@ __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- cluster / cta_group::2 helpers (a CTA pair = two SMs of one TPC sharing one 256-row MMA)
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> rank 0's copy
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER's mbarrier.
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit: arrive on the same barrier offset in BOTH CTAs of the pair once the issued MMAs have retired
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 template <int BLOCK_N, bool OUT_F32>
 struct GemmTmaCfg {
   static constexpr int kABytes = kBlockM * kBlockK * 2;
@@ -68,7 +120,8 @@ template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE, int NBUF = 2>
 __device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, const EpiTmaParams& ep, uint32_t tmem_base,
                                                   uint64_t* tfull_bar, uint64_t* tempty_bar, int as, uint32_t aphase,
                                                   int tile_m0, int tile_n0, int N, int q, int half, int lane,
-                                                  uint8_t* stg, int warp_stg_bytes, int& buf) {
+                                                  uint8_t* stg, int warp_stg_bytes, int& buf,
+                                                  bool tempty_on_leader = false) {
   constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per half
   const int m0 = tile_m0 + q * 32;
   const int n0 = tile_n0 + half * (BLOCK_N / 2);
@@ -101,7 +154,10 @@ __device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, cons
     } else {
       tcgen05_fence_before();  // accumulator fully read: hand the TMEM buffer back to the MMA warp
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (tempty_on_leader) mbar_arrive_leader(&tempty_bar[as]);  // 2-CTA pair: the issuing CTA owns the barrier
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
     float y[32];
 #pragma unroll
@@ -417,6 +473,145 @@ gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   tcgen05_fence_before();
   __syncthreads();
   if (warp_idx == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) compute one 256 x BLOCK_N tile: each loads its own 128 rows of A
+// and HALF of the weight tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared
+// memory, and each CTA drains its own 128 accumulator rows from its own TMEM.  Per CTA and k-block only
+// 16 KB + BLOCK_N/2 x 128 B enter shared memory (vs 16 KB + BLOCK_N x 128 B), which halves the B-operand share of
+// the smem write + read traffic that bounds the single-CTA kernel at ~55 % tensor-pipe activity, and deepens the
+// TMA look-ahead (6-7 stages instead of 4).
+template <int BLOCK_N, bool OUT_F32>
+struct GemmPairCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kWarpStagingBytes = 32 * 32 * (OUT_F32 ? 4 : 2);
+  static constexpr int kStagingTotal = 16 * kWarpStagingBytes;
+  static constexpr int kBarrierBytes = 512;
+  static constexpr int kStagesRaw = (kSmemLimit - 1024 - kBarrierBytes - kStagingTotal) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingTotal + kBarrierBytes + 1024;
+  static constexpr int kTmemCols = GemmCfg<BLOCK_N>::kTmemCols;
+  static_assert(BLOCK_N % 32 == 0 && kStages >= 3, "bad pair configuration");
+};
+
+template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                    const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiTmaParams ep) {
+  using Cfg = GemmPairCfg<BLOCK_N, OUT_F32>;
+  constexpr int STAGES = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * Cfg::kABytes;
+  uint8_t* smem_c = smem + STAGES * Cfg::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStagingTotal);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader's arrive.expect_tx; bytes arrive from both CTAs' TMA loads
+      mbar_init(&empty_bar[i], 1);  // one multicast commit per round
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);  // 8 epilogue warps of each CTA arrive on the LEADER's barrier
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish_2sm();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // barrier inits of both CTAs visible before any remote arrive / multicast commit
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int num_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp_idx == 0) {
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / num_n) * 2 * kBlockM + rank * kBlockM;
+        const int n0 = (tile % num_n) * BLOCK_N + rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          tma_load_2d_2sm(&tma_a, &full_bar[stage], smem_a + stage * Cfg::kABytes, kb * kBlockK, m0);
+          tma_load_2d_2sm(&tma_b, &full_bar[stage], smem_b + stage * Cfg::kBBytes, kb * kBlockK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (rank == 0 && elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tfull_bar[as]);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int q = warp_idx & 3;
+    const int half = (warp_idx - 4) >> 2;
+    uint8_t* stg = smem_c + (warp_idx - 4) * 2 * Cfg::kWarpStagingBytes;
+    int buf = 0;
+    int local = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      tma_epilogue_tile<BLOCK_N, ACT, OUT_F32, REDUCE>(tma_c, ep, tmem_base, tfull_bar, tempty_bar, as, aphase,
+                                                        (tile / num_n) * 2 * kBlockM + rank * kBlockM,
+                                                        (tile % num_n) * BLOCK_N, N, q, half, lane, stg,
+                                                        Cfg::kWarpStagingBytes, buf, /*tempty_on_leader=*/true);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();  // the peer's barriers / smem stay alive until the leader's last multicast has landed
+  if (warp_idx == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
 }  // namespace effocr
