@@ -202,8 +202,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       mbar_wait(&s_full[g], par);
       tcgen05_fence_after();
       // pass 1: row maximum over the 197 valid keys (chunk c+1 in flight while chunk c is reduced)
-      float mx = -INFINITY;
+      float mx;
       {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: FMNMX latency, not count
         uint32_t v[2][32];
         uint32_t vt[16];
         tmem_ld_32x32b_x32(trow, v[0]);
@@ -213,16 +214,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
           if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
           else tmem_ld_32x32b_x16(trow + 192, vt);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[c & 1][i]));
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c & 1][i]));
         }
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 5; ++i) mx = fmaxf(mx, __uint_as_float(vt[i]));  // keys 192..196
+        for (int i = 0; i < 5; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(vt[i]));  // keys 192..196
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
       const float moff = mx * scale_log2e;
       // pass 2: p = 2^(s * scale - max * scale), row sum, P -> smem (fp16, K-major, swizzled)
-      float sum = 0.f;
+      float sum;
       {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t v[2][32];
         uint32_t vt[16];
         tmem_ld_32x32b_x32(trow, v[0]);
@@ -235,7 +238,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             p[i] = ex2_approx(fmaf(__uint_as_float(v[c & 1][i]), scale_log2e, -moff));
-            sum += p[i];
+            s4[i & 3] += p[i];
           }
           uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
 #pragma unroll
@@ -253,8 +256,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           p[i] = (i < 5) ? ex2_approx(fmaf(__uint_as_float(vt[i]), scale_log2e, -moff)) : 0.f;  // keys >= 197 masked
-          sum += p[i];
+          s4[i & 3] += p[i];
         }
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           uint4 pk;
@@ -274,32 +278,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       tcgen05_fence_after();
       const float inv = 1.0f / sum;
       const int tok = g * 128 + r;
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(trow, o0);
-      tmem_ld_32x32b_x32(trow + 32, o1);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_free[g]);
-      if (tok < kAtT) {
-        __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
+      __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            ph[t] = __floats2half2_rn(__uint_as_float(o0[8 * j + 2 * t]) * inv, __uint_as_float(o0[8 * j + 2 * t + 1]) * inv);
-          *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(trow + hh * 32, o);
+        tmem_ld_wait();
+        if (hh == 1) {  // O fully read: region g is free for the next pair's S
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_free[g]);
         }
+        if (tok < kAtT) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          __half2* ph = reinterpret_cast<__half2*>(&pk);
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            ph[t] = __floats2half2_rn(__uint_as_float(o1[8 * j + 2 * t]) * inv, __uint_as_float(o1[8 * j + 2 * t + 1]) * inv);
-          *reinterpret_cast<uint4*>(dst + 32 + 8 * j) = pk;
+            for (int t = 0; t < 4; ++t)
+              ph[t] = __floats2half2_rn(__uint_as_float(o[8 * j + 2 * t]) * inv, __uint_as_float(o[8 * j + 2 * t + 1]) * inv);
+            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * j) = pk;
+          }
         }
       }
     }

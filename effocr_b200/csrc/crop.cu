@@ -108,22 +108,31 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
         }
         s_src[idx] = px;
       }
+      // tables are stored transposed, index (j % 8) * 28 + j / 8: a warp's lanes own consecutive column octets, so
+      // for a fixed k = j % 8 they read consecutive entries (16-byte lane stride) instead of a 128-byte stride
       for (int j = threadIdx.x; j < OUT; j += blockDim.x) {
         const AxisTaps tx = make_taps(j, scale, support, invscale, S);
-        s_xmn[j] = tx.mn;
-        s_xw[j] = make_float4(tx.sz > 0 ? tap_weight(tx, 0, invscale) : 0.f, tx.sz > 1 ? tap_weight(tx, 1, invscale) : 0.f,
+        const int slot = (j & 7) * 28 + (j >> 3);
+        s_xmn[slot] = tx.mn;
+        s_xw[slot] = make_float4(tx.sz > 0 ? tap_weight(tx, 0, invscale) : 0.f, tx.sz > 1 ? tap_weight(tx, 1, invscale) : 0.f,
                               tx.sz > 2 ? tap_weight(tx, 2, invscale) : 0.f, tx.sz > 3 ? tap_weight(tx, 3, invscale) : 0.f);
       }
       __syncthreads();
       const AxisTaps ty = make_taps(i, scale, support, invscale, S);
+      float wys[4];
+#pragma unroll
+      for (int yy = 0; yy < 4; ++yy) wys[yy] = yy < ty.sz ? tap_weight(ty, yy, invscale) : 0.f;
+      const int oct = j0 >> 3;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const int xmn = s_xmn[j0 + k];
-        const float4 xw = s_xw[j0 + k];
+        const int xmn = s_xmn[k * 28 + oct];
+        const float4 xw = s_xw[k * 28 + oct];
         const float wxs[4] = {xw.x, xw.y, xw.z, xw.w};
         float r = 0.f, g = 0.f, b = 0.f;
-        for (int yy = 0; yy < ty.sz; ++yy) {
-          const float wy = tap_weight(ty, yy, invscale);
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy) {
+          if (yy >= ty.sz) break;
+          const float wy = wys[yy];
           const float4* rowp = s_src + (ty.mn - r0 + yy) * S;
           float rr = 0.f, gg = 0.f, bb = 0.f;
 #pragma unroll

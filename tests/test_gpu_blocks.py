@@ -23,10 +23,14 @@ def _rel(a, b):
     (20000, 1152, 384, 0, 0, False, False, 0),   # many tiles per CTA: phase wrap of both pipelines
     (50000, 1152, 384, 0, 0, False, False, 0),   # A-stationary schedule (K <= 384, >= 2 row blocks per SM)
     (45000, 1536, 384, 1, 0, False, False, 0),
-    (40000, 600, 320, 2, 0, False, False, 0),    # A-stationary with ragged N and K tail
+    (40000, 600, 320, 2, 0, False, False, 0),    # ragged N and K tail on the CTA-pair / A-stationary schedules
+    (30011, 1152, 384, 0, 0, False, False, 0x20000),   # single-CTA TMA epilogue (A-stationary off, pair off)
+    (30011, 384, 1536, 0, 1, False, False, 0x20000),
 ])
 @pytest.mark.parametrize("direct", [False, True])
 def test_gemm_epilogues(M, N, K, act, f32, resid, gamma, bn, direct):
+    """Default dispatch = CTA-pair (cta_group::2) kernel for wide N and many tiles, single-CTA TMA-epilogue kernel
+    otherwise; direct=True forces the first-generation direct-store epilogue."""
     from effocr_b200 import ops
     torch.manual_seed(0)
     a = (torch.randn(M, K, device="cuda") * 0.5).half()
