@@ -11,6 +11,9 @@
 //                   [key][dim] in memory: no transpose pass); fp32 O in TMEM, aliased onto S_g's columns
 //   epilogue        O / rowsum -> fp16 -> global, rows < 197 only
 //
+// The MMA warp issues S0(i), PV1(i-1), S1(i), PV0(i): the two groups run half a period out of phase, so the MUFU-bound
+// softmax of one tile overlaps the MMAs / TMEM waits / epilogue of the other.
+//
 // Q, K, V tiles come straight out of the fused QKV GEMM's output ([B*197, 3*H*64] fp16) by TMA; K of the next
 // pair is prefetched (double buffer), V is single-buffered (its reload hides behind the next pair's S + softmax).
 // Keys 197..207 of a K/V box belong to the next image (or are zero-filled at the end of the tensor); they are
@@ -147,43 +150,56 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       }
     }
   } else if (warp_idx == 1) {
-    // ---------------- MMA issuer
+    // ---------------- MMA issuer.  Issue order per pair i:  S0(i), PV1(i-1), S1(i), PV0(i)  -- the two query-tile
+    // groups run half a period out of phase, so one group's MUFU-bound softmax overlaps the other group's MMAs,
+    // TMEM waits and epilogue instead of both groups competing for the MUFU pipe and then idling together.
     if (elect_one_sync()) {
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
       constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
+      auto issue_s = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        const int s = it & 1;
+        mbar_wait(&q_full[g], par);
+        mbar_wait(&t_free[g], par ^ 1);  // region g (S/O columns) drained by the previous pair's epilogue
+        tcgen05_fence_after();
+        const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + g * kAtQBytes));
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem_k + s * kAtKVBytes));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(&q_empty[g]);
+        umma_commit(&s_full[g]);
+      };
+      auto issue_pv = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        mbar_wait(&p_full[g], par);  // all four warps of the group have read S_g and written P_g
+        tcgen05_fence_after();
+        const uint32_t pbase = smem_u32(smem_p + g * kAtPBytes);
+#pragma unroll
+        for (int ks = 0; ks < 12; ++ks) {
+          const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+          const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem_v + ks * 2048));
+          umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+        }
+        umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
+                 make_sw128_mnmajor_desc(smem_u32(smem_v + 12 * 2048)), idesc_o, 1u);
+        umma_commit(&o_full[g]);
+      };
       int it = 0;
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
         const int s = it & 1;
-        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
-        mbar_wait(&k_full[s], par2);
-        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem_k + s * kAtKVBytes));
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&q_full[g], par);
-          mbar_wait(&t_free[g], par ^ 1);  // region g (S/O columns) drained by the previous pair's epilogue
-          tcgen05_fence_after();
-          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + g * kAtQBytes));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-          umma_commit(&q_empty[g]);
-          umma_commit(&s_full[g]);
+        mbar_wait(&k_full[s], (it >> 1) & 1);
+        issue_s(0, it);
+        if (it > 0) {
+          issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
+          umma_commit(v_empty);
         }
+        issue_s(1, it);
         umma_commit(&k_empty[s]);
-        mbar_wait(v_full, par);
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_full[g], par);  // all four warps of the group have read S_g and written P_g
-          tcgen05_fence_after();
-          const uint32_t pbase = smem_u32(smem_p + g * kAtPBytes);
-#pragma unroll
-          for (int ks = 0; ks < 12; ++ks) {
-            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
-            const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem_v + ks * 2048));
-            umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
-          }
-          umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
-                   make_sw128_mnmajor_desc(smem_u32(smem_v + 12 * 2048)), idesc_o, 1u);
-          umma_commit(&o_full[g]);
-        }
+        mbar_wait(v_full, it & 1);  // V(it), reloaded after PV1(it-1) retired
+        issue_pv(0, it);
+      }
+      if (it > 0) {
+        issue_pv(1, it - 1);
         umma_commit(v_empty);
       }
     }

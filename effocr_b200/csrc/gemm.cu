@@ -155,6 +155,7 @@ static bool use_pair(int bn, const GemmArgs& a) {
   const int num_m = (a.M + 2 * kBlockM - 1) / (2 * kBlockM);
   // measured on B200 (tools/gpu_pair_selftest.py, M = 201 728): QKV +7 %, fc1 (no act) +15 %, fc2 (K = 1536) +20 %,
   // GELU fc1 and the HBM-bound proj unchanged
+  if (a.act == ACT_GELU && a.epilogue != 3) return false;  // the GELU epilogue paces fc1; the pair schedule is 10 % slower there
   return (bn == 192 || bn == 256) && num_m * ((a.N + bn - 1) / bn) >= sm_count() / 2;
 }
 
