@@ -36,16 +36,6 @@ constexpr int kAtThreads = 384;
 constexpr int kAtSmemBytes = 2 * kAtQBytes + 3 * kAtKVBytes + 2 * kAtPBytes + 256 + 1024;
 constexpr uint32_t kAtTmemRegion = 256;   // columns per query-tile group (S: 208, O aliases the first 64)
 
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
 // MN-major operand tile with 128-byte rows written by TMA (SWIZZLE_128B): row = K index (key), the 128 bytes of
 // a row are 64 consecutive MN elements (head dims).  SBO = 1024 B between groups of 8 K rows; one MN atom only.
 __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {

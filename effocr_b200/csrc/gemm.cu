@@ -99,11 +99,14 @@ static int launch_tma(const GemmArgs& a, cudaStream_t stream) {
 template <int BN, int ACT, bool F32, bool RED>
 static int launch_astat(const GemmArgs& a, cudaStream_t stream) {
   using Cfg = GemmAStatCfg<BN, F32>;
+  // sixteen epilogue warps (16-column chunks) when the epilogue has real math to hide: GELU / SiLU on fp16 outputs
+  constexpr int EPI_WARPS = (!F32 && !RED && ACT != ACT_NONE) ? 16 : 8;
   CUtensorMap ta, tb, tc;
   EFFOCR_TRY(make_tmap_f16_2d(&ta, a.A, a.M, a.K, a.lda, kBlockM));
   EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, a.K, a.ldw, BN));
-  EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, 32, 32, F32 ? 128 : 64));
-  auto kern = gemm_tn_astat_kernel<BN, ACT, F32, RED>;
+  if (EPI_WARPS == 16) EFFOCR_TRY(make_tmap_2d(&tc, a.out, 2, a.M, a.N, a.ldo, 32, 16, 32));
+  else EFFOCR_TRY(make_tmap_2d(&tc, a.out, F32 ? 4 : 2, a.M, a.N, a.ldo, 32, 32, F32 ? 128 : 64));
+  auto kern = gemm_tn_astat_kernel<BN, ACT, F32, RED, EPI_WARPS>;
   static bool attr_done = false;
   if (!attr_done) {
     EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -116,7 +119,7 @@ static int launch_astat(const GemmArgs& a, cudaStream_t stream) {
   ep.gamma = a.gamma;
   {
     KernelScope ks(a.prof_tag, stream);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
+    kern<<<grid, 128 + 32 * EPI_WARPS, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

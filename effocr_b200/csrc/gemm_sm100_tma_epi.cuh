@@ -205,6 +205,82 @@ __device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, cons
   }
 }
 
+// Epilogue of one tile for ONE of SIXTEEN epilogue warps (lane quarter q, column quarter cq), 16-column chunks:
+// twice the warps of tma_epilogue_tile with half the registers each, for epilogues whose math (GELU) would otherwise
+// pace the tile -- four warps per scheduler hide the TMEM-load and MUFU latencies that two cannot.  fp16 output only.
+template <int BLOCK_N, int ACT>
+__device__ __forceinline__ void tma_epilogue_tile16(const CUtensorMap& tma_c, const EpiTmaParams& ep, uint32_t tmem_base,
+                                                    uint64_t* tfull_bar, uint64_t* tempty_bar, int as, uint32_t aphase,
+                                                    int tile_m0, int tile_n0, int N, int q, int cq, int lane, uint8_t* stg,
+                                                    int& buf) {
+  constexpr int CHUNKS = BLOCK_N / 64;  // 16-column chunks per warp
+  const int m0 = tile_m0 + q * 32;
+  const int n0 = tile_n0 + cq * (BLOCK_N / 4);
+  const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cq * (BLOCK_N / 4);
+  mbar_wait(&tfull_bar[as], aphase);
+  tcgen05_fence_after();
+  uint32_t v[2][16];
+  tmem_ld_32x32b_x16(tbase, v[0]);
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col0 = n0 + c * 16;
+    float bv[16];
+    if (ep.bias) {
+      if (col0 + 16 <= N) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(ep.bias + col0 + i));
+          bv[i] = b.x; bv[i + 1] = b.y; bv[i + 2] = b.z; bv[i + 3] = b.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bv[i] = (col0 + i < N) ? __ldg(ep.bias + col0 + i) : 0.f;
+      }
+    }
+    tmem_ld_wait();
+    if (c + 1 < CHUNKS) {
+      tmem_ld_32x32b_x16(tbase + (c + 1) * 16, v[(c + 1) & 1]);
+    } else {
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float t = __uint_as_float(v[c & 1][i]);
+      if (ep.bias) t += bv[i];
+      if (ACT == ACT_GELU) t = gelu_erf(t);
+      if (ACT == ACT_SILU) t = silu(t);
+      y[i] = t;
+    }
+    if (ep.gamma) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (col0 + i < N) y[i] *= __ldg(ep.gamma + col0 + i);
+    }
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* dst = stg + buf * 1024;
+    // 32-byte rows, SWIZZLE_32B: 16-byte piece j of row r lives at piece j ^ ((r >> 2) & 1)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint4 pk;
+      __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+      *reinterpret_cast<uint4*>(dst + lane * 32 + ((j ^ ((lane >> 2) & 1)) << 4)) = pk;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&tma_c, dst, col0, m0);
+      tma_store_commit();
+    }
+    buf ^= 1;
+  }
+}
+
 // ACT: activation; OUT_F32: output element type; REDUCE: TMA reduce-add into the output (in-place residual)
 template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -351,8 +427,8 @@ struct GemmAStatCfg {
   static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BLOCK_N, int ACT, bool OUT_F32, bool REDUCE, int EPI_WARPS = 8>
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1)
 gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                      const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, EpiTmaParams ep) {
   using Cfg = GemmAStatCfg<BLOCK_N, OUT_F32>;
@@ -382,7 +458,7 @@ gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
   if (warp_idx == 1 && elect_one_sync()) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&bfull_bar[i], 1); mbar_init(&bempty_bar[i], 1); }
     for (int i = 0; i < MAXKB; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -452,6 +528,21 @@ gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
           umma_commit(&tfull_bar[as]);
         }
       }
+    }
+  } else if (warp_idx >= 4 && EPI_WARPS == 16) {
+    if constexpr (!OUT_F32 && !REDUCE) {
+      const int q = warp_idx & 3;
+      const int cq = (warp_idx - 4) >> 2;
+      uint8_t* stg = smem_c + (warp_idx - 4) * 2048;
+      int buf = 0;
+      int local = 0;
+      for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x) {
+        for (int nb = 0; nb < num_n; ++nb, ++local) {
+          tma_epilogue_tile16<BLOCK_N, ACT>(tma_c, ep, tmem_base, tfull_bar, tempty_bar, local & 1, (local >> 1) & 1,
+                                            mb * kBlockM, nb * BLOCK_N, N, q, cq, lane, stg, buf);
+        }
+      }
+      if (lane == 0) tma_store_wait_all<0>();
     }
   } else if (warp_idx >= 4) {
     const int q = warp_idx & 3;
