@@ -48,6 +48,10 @@ SIGNATURES = {
     "effocr_vit_max_batch": (c_int, [c_void_p]),
     "effocr_vit_patch_buffer": (c_void_p, [c_void_p]),
     "effocr_vit_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_convnext_create": (c_int, [c_int, c_void_p, c_int, c_void_p]),
+    "effocr_convnext_destroy": (None, [c_void_p]),
+    "effocr_convnext_patch_buffer": (c_void_p, [c_void_p]),
+    "effocr_convnext_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_layernorm": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_float, c_int,
                                  c_void_p]),
     "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -55,7 +55,7 @@ __device__ __forceinline__ void numpy_slice(int start, int stop, int n, int* lo,
 constexpr int kCropMaxStage = 3072;  // staged source pixels (float4 each) per block: 48 KB
 constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4;
 
-template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16)
+template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16), 3 4x4-patch-major f16 ([n*3136, 48])
 __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restrict__ pixels,
                                                           const effocr_image_desc* __restrict__ images,
                                                           const effocr_crop_box* __restrict__ boxes, int n_boxes,
@@ -191,6 +191,17 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
       float* o = reinterpret_cast<float*>(out) + ((static_cast<long long>(n) * 3 + c) * OUT + i) * OUT + j0;
       *reinterpret_cast<float4*>(o) = make_float4(acc[c][0], acc[c][1], acc[c][2], acc[c][3]);
       *reinterpret_cast<float4*>(o + 4) = make_float4(acc[c][4], acc[c][5], acc[c][6], acc[c][7]);
+    } else if (LAYOUT == 3) {
+      // ConvNeXt stem im2col: row = n*3136 + (i/4)*56 + j/4, col = c*16 + (i%4)*4 + j%4; 8 columns = two patches
+      const long long row = static_cast<long long>(n) * 3136 + (i >> 2) * 56 + (j0 >> 2);
+      __half* o = reinterpret_cast<__half*>(out) + row * 48 + c * 16 + (i & 3) * 4;
+      uint2 p0, p1;
+      *reinterpret_cast<__half2*>(&p0.x) = __floats2half2_rn(acc[c][0], acc[c][1]);
+      *reinterpret_cast<__half2*>(&p0.y) = __floats2half2_rn(acc[c][2], acc[c][3]);
+      *reinterpret_cast<__half2*>(&p1.x) = __floats2half2_rn(acc[c][4], acc[c][5]);
+      *reinterpret_cast<__half2*>(&p1.y) = __floats2half2_rn(acc[c][6], acc[c][7]);
+      *reinterpret_cast<uint2*>(o) = p0;
+      *reinterpret_cast<uint2*>(o + 48) = p1;
     } else {
       uint4 pk;
       *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(acc[c][0], acc[c][1]);
@@ -227,6 +238,7 @@ extern "C" int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
     EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
     EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
     EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
+    EFFOCR_CUDA(cudaFuncSetAttribute(crop_resize_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCropSmemBytes));
     attr = true;
   }
   KernelScope ks(PROF_CROP, s);
@@ -234,6 +246,7 @@ extern "C" int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
     case EFFOCR_CROP_NCHW_F16: crop_resize_kernel<0><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
     case EFFOCR_CROP_NCHW_F32: crop_resize_kernel<1><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
     case EFFOCR_CROP_PATCH_F16: crop_resize_kernel<2><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
+    case EFFOCR_CROP_PATCH4_F16: crop_resize_kernel<3><<<grid, 224, kCropSmemBytes, s>>>(d_pixels, d_images, d_boxes, n_boxes, d_out); break;
     default: return fail(EFFOCR_ERR_INVALID, "crop_resize: unknown layout");
   }
   EFFOCR_CUDA(cudaGetLastError());

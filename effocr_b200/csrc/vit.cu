@@ -75,11 +75,11 @@ static int layernorm_launch(const float* x, long long ldx, const float* g, const
 }
 
 int layernorm_f16(const float* x, long long ldx, const float* g, const float* b, __half* out, long long ldo, int rows,
-                  int D, float eps, cudaStream_t s, int tag = PROF_LAYERNORM) {
+                  int D, float eps, cudaStream_t s, int tag) {
   return layernorm_launch<__half>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 int layernorm_f32(const float* x, long long ldx, const float* g, const float* b, float* out, long long ldo, int rows,
-                  int D, float eps, cudaStream_t s, int tag = PROF_FINAL_LN) {
+                  int D, float eps, cudaStream_t s, int tag) {
   return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 
@@ -133,7 +133,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
   EFFOCR_CUDA(cudaGetLastError());
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
-    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s));
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
     g = GemmArgs();
     g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
     g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
@@ -143,7 +143,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
     g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
     EFFOCR_TRY(gemm_f16(g, s));
-    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s));
+    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
     g = GemmArgs();
     g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = M; g.N = v->mlp; g.K = D;
     g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1; g.prof_tag = PROF_GEMM_FC1;
@@ -154,7 +154,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     EFFOCR_TRY(gemm_f16(g, s));
   }
   // final LayerNorm on the CLS rows only (row stride T * D)
-  EFFOCR_TRY(layernorm_f32(v->x, static_cast<long long>(T) * D, v->lnf_w, v->lnf_b, emb, D, B, D, v->eps, s));
+  EFFOCR_TRY(layernorm_f32(v->x, static_cast<long long>(T) * D, v->lnf_w, v->lnf_b, emb, D, B, D, v->eps, s, PROF_FINAL_LN));
   return EFFOCR_OK;
 }
 
@@ -262,8 +262,8 @@ extern "C" int effocr_layernorm(const float* d_x, long long ldx, const float* d_
   EFFOCR_TRY(require_sm100());
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (rows <= 0) return EFFOCR_OK;
-  return out_f32 ? layernorm_f32(d_x, ldx, d_gamma, d_beta, reinterpret_cast<float*>(d_out), ldo, rows, dim, eps, s)
-                 : layernorm_f16(d_x, ldx, d_gamma, d_beta, reinterpret_cast<__half*>(d_out), ldo, rows, dim, eps, s);
+  return out_f32 ? layernorm_f32(d_x, ldx, d_gamma, d_beta, reinterpret_cast<float*>(d_out), ldo, rows, dim, eps, s, PROF_LAYERNORM)
+                 : layernorm_f16(d_x, ldx, d_gamma, d_beta, reinterpret_cast<__half*>(d_out), ldo, rows, dim, eps, s, PROF_LAYERNORM);
 }
 
 extern "C" int effocr_attention_f16(const void* d_qkv, void* d_out, int batch, int tokens, int heads, int impl,

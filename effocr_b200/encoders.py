@@ -18,7 +18,7 @@ from collections import OrderedDict
 import torch
 
 from . import _lib
-from .engine import VIT_CONFIGS, VitEngine
+from .engine import CONVNEXT_DEPTHS, CONVNEXT_DIMS, VIT_CONFIGS, ConvNextEngine, VitEngine
 
 _TIMM_ALIASES = {
     "vit_tiny_patch16_224.augreg_in21k_ft_in1k": "vit_tiny_patch16_224",
@@ -67,6 +67,44 @@ class TimmViTParams(torch.nn.Module):
         self.num_features = self.embed_dim = d
 
 
+class TimmConvNeXtParams(torch.nn.Module):
+    """Parameter container with timm convnext_tiny's parameter names and shapes (timm init: trunc_normal .02,
+    zero bias, layer-scale gamma 1e-6)."""
+
+    def __init__(self, name: str = "convnext_tiny"):
+        super().__init__()
+        if name.split(".")[0] != "convnext_tiny":
+            raise NotImplementedError(f"encoder '{name}' is not implemented in effocr_b200")
+        self.arch = "convnext_tiny"
+        nn = torch.nn
+
+        def init(m):
+            torch.nn.init.trunc_normal_(m.weight, std=0.02)
+            torch.nn.init.zeros_(m.bias)
+            return m
+
+        self.stem = nn.Sequential(init(nn.Conv2d(3, 96, 4, 4)), nn.LayerNorm(96, eps=1e-6))
+        self.stages = nn.ModuleList()
+        for i, (depth, dim) in enumerate(zip(CONVNEXT_DEPTHS, CONVNEXT_DIMS)):
+            st = nn.Module()
+            st.downsample = nn.Identity() if i == 0 else nn.Sequential(nn.LayerNorm(CONVNEXT_DIMS[i - 1], eps=1e-6),
+                                                                         init(nn.Conv2d(CONVNEXT_DIMS[i - 1], dim, 2, 2)))
+            st.blocks = nn.ModuleList()
+            for _ in range(depth):
+                b = nn.Module()
+                b.conv_dw = init(nn.Conv2d(dim, dim, 7, padding=3, groups=dim))
+                b.norm = nn.LayerNorm(dim, eps=1e-6)
+                b.mlp = nn.Module()
+                b.mlp.fc1 = init(nn.Linear(dim, 4 * dim))
+                b.mlp.fc2 = init(nn.Linear(4 * dim, dim))
+                b.gamma = nn.Parameter(torch.full((dim,), 1e-6))
+                st.blocks.append(b)
+            self.stages.append(st)
+        self.head = nn.Module()
+        self.head.norm = nn.LayerNorm(768, eps=1e-6)
+        self.num_features = 768
+
+
 def hf_vit_to_timm(hf_sd, prefix: str = "") -> "OrderedDict[str, torch.Tensor]":
     """transformers.ViTModel state dict -> timm names (the mapping the reference documents in
     scripts/trocr_fairseq_to_pytorch_chkpt.py:30-88, inverted); fused qkv rows are [q | k | v]."""
@@ -109,11 +147,15 @@ class _EngineBackedEncoder(torch.nn.Module):
     def _params_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def engine(self) -> VitEngine:
+    def engine(self):
         ver = self._params_version()
         if getattr(self, "_engine", None) is None or self._engine_ver != ver:
             sd = {"net." + k: v for k, v in self._timm_state().items()}
-            object.__setattr__(self, "_engine", VitEngine(sd, prefix="net.", max_batch=self.max_batch, ln_eps=self.ln_eps))
+            if "net.stem.0.weight" in sd:
+                eng = ConvNextEngine(sd, prefix="net.", max_batch=min(self.max_batch, 256))
+            else:
+                eng = VitEngine(sd, prefix="net.", max_batch=self.max_batch, ln_eps=self.ln_eps)
+            object.__setattr__(self, "_engine", eng)
             object.__setattr__(self, "_engine_ver", ver)
         return self._engine
 
@@ -136,7 +178,7 @@ def AutoEncoderFactory(backend, modelpath):
 
             def __init__(self, model=modelpath, device="cuda"):
                 super().__init__()
-                net = TimmViTParams(model)
+                net = TimmConvNeXtParams(model) if str(model).startswith("convnext") else TimmViTParams(model)
                 if device != "cpu" and torch.cuda.is_available():
                     net.to(device)
                 self.net = net

@@ -99,6 +99,86 @@ class VitEngine:
     __call__ = forward
 
 
+CONVNEXT_DEPTHS, CONVNEXT_DIMS = (3, 3, 9, 3), (96, 192, 384, 768)
+
+
+def convnext_weight_order():
+    keys = ["stem.0.weight", "stem.0.bias", "stem.1.weight", "stem.1.bias"]
+    for i, depth in enumerate(CONVNEXT_DEPTHS):
+        if i > 0:
+            keys += [f"stages.{i}.downsample.{n}.{w}" for n in (0, 1) for w in ("weight", "bias")]
+        for j in range(depth):
+            p = f"stages.{i}.blocks.{j}."
+            keys += [p + k for k in ("conv_dw.weight", "conv_dw.bias", "norm.weight", "norm.bias", "mlp.fc1.weight",
+                                     "mlp.fc1.bias", "mlp.fc2.weight", "mlp.fc2.bias", "gamma")]
+    return keys + ["head.norm.weight", "head.norm.bias"]
+
+
+class ConvNextEngine:
+    """Device-resident ConvNeXt-Tiny encoder behind effocr_convnext_* (same surface as VitEngine)."""
+
+    embed_dim = 768
+
+    def __init__(self, state_dict, prefix: str = "net.", max_batch: int = 256, device=None):
+        self._lib = _lib.load()
+        if device is not None:
+            torch.cuda.set_device(device)
+        _lib.require_device()
+        sd = {k[len(prefix):]: v for k, v in state_dict.items() if k.startswith(prefix)}
+        keys = convnext_weight_order()
+        missing = [k for k in keys if k not in sd]
+        if missing:
+            raise _lib.EffocrError(f"not a timm convnext_tiny checkpoint (missing {missing[:3]} ...)")
+        keep, ptrs = [], (C.c_void_p * len(keys))()
+        for i, k in enumerate(keys):
+            a = np.ascontiguousarray(sd[k].detach().to("cpu", torch.float32).numpy())
+            keep.append(a)
+            ptrs[i] = a.ctypes.data
+        h = C.c_void_p()
+        _lib.check(self._lib.effocr_convnext_create(int(max_batch), ptrs, len(keys), C.byref(h)), "effocr_convnext_create")
+        self._h = h
+        self.max_batch = int(max_batch)
+        self._lock = threading.Lock()
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.effocr_convnext_destroy(h)
+
+    def patch_buffer(self, n_crops: int) -> torch.Tensor:
+        if n_crops > self.max_batch:
+            raise _lib.EffocrError("patch_buffer: n_crops exceeds max_batch")
+        p = self._lib.effocr_convnext_patch_buffer(self._h)
+        return _tensor_from_ptr(p, (n_crops * 3136, 48), torch.float16, self.device)
+
+    def forward(self, x: torch.Tensor | None, batch: int | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        if x is None:
+            kind, B, p = ops.INPUT_PATCH_BUFFER, int(batch), 0
+        else:
+            x = ops._cuda(x, torch.float32, "x").contiguous()
+            if x.dim() != 4 or tuple(x.shape[1:]) != (3, 224, 224):
+                raise _lib.EffocrError(f"expected [B,3,224,224], got {tuple(x.shape)}")
+            kind, B, p = ops.INPUT_NCHW_F32, x.shape[0], x.data_ptr()
+        if out is None:
+            out = torch.empty((B, 768), device=self.device, dtype=torch.float32)
+        with self._lock:
+            _lib.check(self._lib.effocr_convnext_forward(self._h, p, kind, B, out.data_ptr(), _lib.stream_ptr()),
+                       "effocr_convnext_forward")
+        return out
+
+    __call__ = forward
+
+
+def make_encoder_engine(state_dict, prefix: str = "net.", max_batch: int = 1024):
+    """ViT or ConvNeXt engine, chosen from the checkpoint's keys."""
+    if prefix + "cls_token" in state_dict:
+        return VitEngine(state_dict, prefix=prefix, max_batch=max_batch)
+    if prefix + "stem.0.weight" in state_dict:
+        return ConvNextEngine(state_dict, prefix=prefix, max_batch=min(max_batch, 256))
+    raise _lib.EffocrError("unrecognised encoder checkpoint (expected timm ViT or ConvNeXt keys)")
+
+
 def _tensor_from_ptr(ptr: int, shape, dtype, device) -> torch.Tensor:
     """Wrap library-owned device memory as a torch tensor (no ownership transfer)."""
     n = int(np.prod(shape))

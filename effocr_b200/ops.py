@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
-CROP_NCHW_F16, CROP_NCHW_F32, CROP_PATCH_F16 = 0, 1, 2
+CROP_NCHW_F16, CROP_NCHW_F32, CROP_PATCH_F16, CROP_PATCH4_F16 = 0, 1, 2, 3
 INPUT_NCHW_F32, INPUT_PATCH_F16, INPUT_PATCH_BUFFER = 0, 1, 2
 
 IMAGE_DESC_DTYPE = np.dtype([("offset", "<i8"), ("height", "<i4"), ("width", "<i4"), ("pitch", "<i4"),
@@ -89,6 +89,8 @@ def crop_resize(pixels: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor,
     if out is None:
         if layout == CROP_PATCH_F16:
             out = torch.empty((n_boxes * 196, 768), device=pixels.device, dtype=torch.float16)
+        elif layout == CROP_PATCH4_F16:
+            out = torch.empty((n_boxes * 3136, 48), device=pixels.device, dtype=torch.float16)
         else:
             out = torch.empty((n_boxes, 3, 224, 224), device=pixels.device,
                               dtype=torch.float32 if layout == CROP_NCHW_F32 else torch.float16)

@@ -88,6 +88,7 @@ typedef struct {
 #define EFFOCR_CROP_NCHW_F16 0  /* out: fp16 [n, 3, 224, 224] */
 #define EFFOCR_CROP_NCHW_F32 1  /* out: fp32 [n, 3, 224, 224]  (== create_paired_transform output) */
 #define EFFOCR_CROP_PATCH_F16 2 /* out: fp16 [n * 196, 768] patch-major (input of effocr_vit_forward) */
+#define EFFOCR_CROP_PATCH4_F16 3 /* out: fp16 [n * 3136, 48] 4x4-patch-major (input of effocr_convnext_forward) */
 EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
                                   const effocr_crop_box* d_boxes, int n_boxes, int layout, void* d_out, void* stream);
 
@@ -115,6 +116,21 @@ EFFOCR_API void* effocr_vit_patch_buffer(effocr_vit_t h);
 /* d_emb: fp32 [B, D] pooled pre-logits (final-LayerNorm'd CLS token), NOT L2-normalised. */
 EFFOCR_API int effocr_vit_forward(effocr_vit_t h, const void* d_input, int input_kind, int batch, float* d_emb,
                                   void* stream);
+
+/* ---- recognizer encoder: timm convnext_tiny, num_classes=0 (BASELINE config 4) --------------------
+ * Same call sites as the ViT handle (models/encoders.py:58,62-64).  h_weights: HOST fp32 tensors in timm order
+ * (n_weights = 180): stem.0.weight [96,3,4,4], stem.0.bias, stem.1.weight, stem.1.bias; per stage i = 0..3:
+ * (i > 0: downsample.0.weight, downsample.0.bias, downsample.1.weight [C,Cp,2,2], downsample.1.bias), per block:
+ * conv_dw.weight [C,1,7,7], conv_dw.bias, norm.weight, norm.bias, mlp.fc1.weight [4C,C], mlp.fc1.bias,
+ * mlp.fc2.weight [C,4C], mlp.fc2.bias, gamma [C]; then head.norm.weight, head.norm.bias.
+ * Input kinds: EFFOCR_INPUT_NCHW_F32, or EFFOCR_INPUT_PATCH_BUFFER after effocr_crop_resize wrote
+ * EFFOCR_CROP_PATCH4_F16 rows into effocr_convnext_patch_buffer().  d_emb: fp32 [B, 768]. */
+typedef struct effocr_convnext_s* effocr_convnext_t;
+EFFOCR_API int effocr_convnext_create(int max_batch, const float* const* h_weights, int n_weights, effocr_convnext_t* out);
+EFFOCR_API void effocr_convnext_destroy(effocr_convnext_t h);
+EFFOCR_API void* effocr_convnext_patch_buffer(effocr_convnext_t h);
+EFFOCR_API int effocr_convnext_forward(effocr_convnext_t h, const void* d_input, int input_kind, int batch, float* d_emb,
+                                       void* stream);
 
 /* building blocks of the encoder, exported for the parity tests */
 EFFOCR_API int effocr_layernorm(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta,

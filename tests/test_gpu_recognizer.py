@@ -123,3 +123,62 @@ def test_knn_remove_ids_compacts():
     assert index.ntotal == 48
     _, idx = index.search_device(xb[[2, 4, 11, 49]].cuda(), 1)
     assert idx.cpu().flatten().tolist() == [2, 3, 9, 47]
+
+
+def test_convnext_embeddings_match_oracle():
+    """ConvNeXt-Tiny (BASELINE config 4 encoder): fp16 operands vs the fp32 oracle, chunked batches."""
+    from effocr_b200.engine import ConvNextEngine
+    from oracle import convnext as OC
+    sd = OC.init_convnext_tiny_state_dict(seed=0)
+    x = torch.randn(3, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = OC.convnext_forward(sd, x)
+    eng = ConvNextEngine(sd, max_batch=2)
+    out = eng.forward(x.cuda()).cpu()
+    rel = ((out - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    assert rel <= 2e-3, rel  # 18 blocks of fp16 operands; the ViT bound (1e-3) is asserted for the bench encoder
+
+
+def test_convnext_crop_patch4_path_equals_nchw_path():
+    from effocr_b200 import ops
+    from effocr_b200.engine import ConvNextEngine
+    from oracle import convnext as OC
+    sd = OC.init_convnext_tiny_state_dict(seed=1)
+    eng = ConvNextEngine(sd, max_batch=4)
+    rng = np.random.default_rng(0)
+    crops = _random_crops(rng, 4)
+    pixels, images, _ = ops.pack_images(crops)
+    bt, n = ops.pack_boxes([(i, 0, 0, c.shape[1], c.shape[0]) for i, c in enumerate(crops)])
+    nchw = ops.crop_resize(pixels, images, bt, n, ops.CROP_NCHW_F16).float()
+    e0 = eng.forward(nchw)
+    ops.crop_resize(pixels, images, bt, n, ops.CROP_PATCH4_F16, out=eng.patch_buffer(n))
+    e1 = eng.forward(None, batch=n)
+    assert torch.equal(e0, e1)
+
+
+def test_autoencoder_factory_convnext_and_vit_surface():
+    from effocr_b200.encoders import AutoEncoderFactory
+    for name, dim in (("vit_tiny_patch16_224", 192), ("convnext_tiny", 768)):
+        enc = AutoEncoderFactory("timm", name)(device="cuda").eval()
+        assert any(k.startswith("net.") for k in enc.state_dict())
+        with torch.no_grad():
+            y = enc(torch.randn(2, 3, 224, 224, device="cuda"))
+        assert y.shape == (2, dim) and y.is_cuda and torch.isfinite(y).all()
+
+
+def test_knn_stress_config4_shape():
+    """BASELINE config 4: 50k-glyph index, D = 768, 4096 queries, k = 10 -- score matrix (819 MB) never materialised."""
+    from effocr_b200.engine import FlatIPIndex
+    from oracle import knn as K
+    g = torch.Generator().manual_seed(4)
+    xb = torch.nn.functional.normalize(torch.randn(50000, 768, generator=g) + 1.0, dim=1)
+    q = torch.nn.functional.normalize(torch.randn(4096, 768, generator=g) + 1.0, dim=1)
+    index = FlatIPIndex(768)
+    index.add(xb)
+    dist, idx = index.search_device(q.cuda(), 10)
+    sub = slice(0, 256)  # oracle on a slice (fp64 margins on 256 x 50k)
+    rd, ri = K.flat_ip_search(xb, q[sub], 10)
+    _, margin = K.margins(xb, q[sub], 10)
+    dec = margin > 1e-6
+    assert torch.equal(idx.cpu()[sub][dec], ri[dec])
+    assert torch.allclose(dist.cpu()[sub], rd, atol=3e-6, rtol=0)
