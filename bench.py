@@ -264,7 +264,7 @@ def main():
     if dist is not None:
         dist.broadcast(index_vectors, src=0)
     pipe = RecognizerPipeline.__new__(RecognizerPipeline)
-    pipe.encoder, pipe.max_batch, pipe.candidate_chars = boot.encoder, B, None
+    pipe.encoder, pipe.max_batch, pipe.candidate_chars, pipe._crop_layout = boot.encoder, B, None, boot._crop_layout
     from effocr_b200.engine import FlatIPIndex
 
     pipe.index = FlatIPIndex(D)

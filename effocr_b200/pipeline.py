@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .engine import FlatIPIndex, VitEngine
+from .engine import ConvNextEngine, FlatIPIndex, VitEngine, make_encoder_engine
 
 
 class PackedCrops:
@@ -57,7 +57,9 @@ class RecognizerPipeline:
     def __init__(self, encoder_state, index, candidate_chars=None, max_batch: int = 1024, prefix: str | None = None):
         if prefix is None:
             prefix = "net." if any(k.startswith("net.") for k in encoder_state) else ""
-        self.encoder = VitEngine(encoder_state, prefix=prefix, max_batch=max_batch)
+        self.encoder = make_encoder_engine(encoder_state, prefix=prefix, max_batch=max_batch)  # ViT or ConvNeXt
+        max_batch = self.encoder.max_batch
+        self._crop_layout = ops.CROP_PATCH4_F16 if isinstance(self.encoder, ConvNextEngine) else ops.CROP_PATCH_F16
         if not isinstance(index, FlatIPIndex):
             vec = torch.as_tensor(index, dtype=torch.float32)
             index = FlatIPIndex(vec.shape[1])
@@ -73,7 +75,7 @@ class RecognizerPipeline:
         itemsize = ops.CROP_BOX_DTYPE.itemsize
         for b0 in range(0, n, self.max_batch):
             b = min(self.max_batch, n - b0)
-            ops.crop_resize(pixels, images, boxes[b0 * itemsize:], b, ops.CROP_PATCH_F16, out=self.encoder.patch_buffer(b))
+            ops.crop_resize(pixels, images, boxes[b0 * itemsize:], b, self._crop_layout, out=self.encoder.patch_buffer(b))
             self.encoder.forward(None, batch=b, out=out[b0:b0 + b])
         return ops.l2_normalize(out)
 
