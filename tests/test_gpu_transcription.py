@@ -64,9 +64,11 @@ def test_transcriptions_identical_to_oracle_and_readable():
         pos += n
     acc, cer_vs_ref = textproc.textline_evaluation(pairs_ref)
     assert cer_vs_ref == 0.0 and acc == 100.0, [p for p in pairs_ref if p[0] != p[1]][:3]
-    # top-10 neighbour lists agree wherever the oracle's own ordering is decidable
+    # top-10 neighbour lists agree wherever the oracle's ordering is decidable: here the two arms embed with
+    # different arithmetic (fp16 operands vs fp32), so consecutive scores must differ by 4 x the 1e-3 tolerance
     _, m10 = OK.margins(xb, emb, 10)
-    dec = (m10 > 1e-5).numpy()
-    assert np.array_equal(idx[dec], ri.numpy()[dec])
+    dec = (m10 > 4e-3).numpy()
+    assert dec.any() and np.array_equal(idx[dec], ri.numpy()[dec])
+    assert np.array_equal(idx[:, 0], ri.numpy()[:, 0])  # top-1 ids identical for every character
     _, cer_gt = textproc.textline_evaluation(pairs_gt, no_spaces_in_eval=True)
     assert cer_gt < 0.15, cer_gt  # the quick-fit recogniser reads the synthetic lines
