@@ -148,6 +148,13 @@ def time_cpu_baseline(sd, crops, index_vectors, k, budget_s):
     return n, dt, emb, dist, idx
 
 
+def workload_config(args, world):
+    """The same `config` object on both arms (the driver compares them)."""
+    return {"workload": f"ViT-S/16 recognizer, 224x224 crops, {args.index}-glyph index, batch {args.batch} crops per GPU, k={args.k}",
+            "l2": "per-step activations (1.7 GB) exceed the 126 MB L2; weights (43 MB fp16) stay L2-resident by design",
+            "parallelism": f"dp{world} over crops, index broadcast at start-up"}
+
+
 def run_reference(args):
     """--impl reference: rank 0 only; CPU oracle port, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -174,10 +181,10 @@ def run_reference(args):
         "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"ViT-S/16 recognizer, 224x224 crops, {args.index}-glyph index, k={args.k}; "
-                               f"bounded sample of {sample} crops per step on the host CPU"},
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": "crops/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} crops/step x {args.steps} steps, oracle port (timm/faiss/onnxruntime not installable)"},
+                         "sample": f"bounded sample: {sample} crops of the workload per step x {args.steps} steps on the host CPU, "
+                                   f"oracle port (timm/faiss/onnxruntime not installable)"},
         "e2e": {"value": val, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -408,10 +415,8 @@ def main():
             "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)",
             "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate", "data": "synthetic (Pillow-rendered glyph crops, random-init ViT-S)",
-            "config": {"workload": f"ViT-S/16 recognizer, 224x224 crops, {args.index}-glyph index, batch {B} crops per GPU, k={K}",
-                       "l2": "per-step activations (1.7 GB) exceed the 126 MB L2; weights (43 MB fp16) stay L2-resident by design",
-                       "parallelism": f"dp{world} over crops, index broadcast at start-up"},
+            "dtype": "f16", "numerics": "f16 operands, f32 accumulate / residual stream / LayerNorm / softmax", "data": "synthetic (Pillow-rendered glyph crops, random-init ViT-S)",
+            "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": packed.h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -42,6 +42,7 @@ SIGNATURES = {
     "effocr_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_letterbox_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "effocr_vit_destroy": (None, [c_void_p]),
     "effocr_vit_embed_dim": (c_int, [c_void_p]),

@@ -62,6 +62,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {
   return make_idesc_f16(M, N) | (1u << 16);
 }
 
+template <bool kSinglePass>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
                     __half* __restrict__ out, int batch, int H, float scale_log2e) {
@@ -207,104 +208,174 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
       const uint32_t par = it & 1;
       mbar_wait(&s_full[g], par);
       tcgen05_fence_after();
-      // Pass 1 -- the ONLY pass over TMEM (tcgen05.ld moves 64 B/clk/SM; reading S twice was the kernel's bound):
-      // t = s * scale (log2 domain), running row maximum m, and the DELTAS d = t - m (<= 0) go to the P tile as
-      // fp16, each 32-key chunk relative to the running maximum at that point (ref[c]).  fp16 keeps |d| * 2^-11
-      // absolute precision, i.e. the entries that matter (d near 0) are accurate to ~1e-4 in the exponent.
-      float ref[7];
-      float mrun = -INFINITY;
-      {
-        uint32_t v[2][32];
-        uint32_t vt[16];
-        tmem_ld_32x32b_x32(trow, v[0]);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          tmem_ld_wait();
-          if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
-          else tmem_ld_32x32b_x16(trow + 192, vt);
-          float t[32];
-          float m4[4] = {mrun, mrun, mrun, mrun};
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            t[i] = __uint_as_float(v[c & 1][i]) * scale_log2e;
-            m4[i & 3] = fmaxf(m4[i & 3], t[i]);
+      float sum;
+      if constexpr (kSinglePass) {
+        // Pass 1 -- the ONLY pass over TMEM (tcgen05.ld moves 64 B/clk/SM; reading S twice was the kernel's bound):
+        // t = s * scale (log2 domain), running row maximum m, and the DELTAS d = t - m (<= 0) go to the P tile as
+        // fp16, each 32-key chunk relative to the running maximum at that point (ref[c]).  fp16 keeps |d| * 2^-11
+        // absolute precision, i.e. the entries that matter (d near 0) are accurate to ~1e-4 in the exponent.
+        float ref[7];
+        float mrun = -INFINITY;
+        {
+          uint32_t v[2][32];
+          uint32_t vt[16];
+          tmem_ld_32x32b_x32(trow, v[0]);
+  #pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+            else tmem_ld_32x32b_x16(trow + 192, vt);
+            float t[32];
+            float m4[4] = {mrun, mrun, mrun, mrun};
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              t[i] = __uint_as_float(v[c & 1][i]) * scale_log2e;
+              m4[i & 3] = fmaxf(m4[i & 3], t[i]);
+            }
+            mrun = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+            ref[c] = mrun;
+            uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __half2* ph = reinterpret_cast<__half2*>(&pk);
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) ph[u] = __floats2half2_rn(t[8 * j + 2 * u] - mrun, t[8 * j + 2 * u + 1] - mrun);
+              const int piece = (c & 1) * 4 + j;  // 16-byte piece inside the 64-key chunk
+              *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk;
+            }
           }
-          mrun = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          ref[c] = mrun;
-          uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          tmem_ld_wait();
+          float t[16];
+  #pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            t[i] = (i < 5) ? __uint_as_float(vt[i]) * scale_log2e : -INFINITY;  // keys >= 197 masked
+            mrun = fmaxf(mrun, t[i]);
+          }
+          ref[6] = mrun;
+  #pragma unroll
+          for (int j = 0; j < 2; ++j) {
             uint4 pk;
             __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
+  #pragma unroll
             for (int u = 0; u < 4; ++u) ph[u] = __floats2half2_rn(t[8 * j + 2 * u] - mrun, t[8 * j + 2 * u + 1] - mrun);
-            const int piece = (c & 1) * 4 + j;  // 16-byte piece inside the 64-key chunk
-            *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk;
+            *reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4)) = pk;  // SWIZZLE_32B: bit 4 ^= bit 7
           }
         }
-        tmem_ld_wait();
-        float t[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          t[i] = (i < 5) ? __uint_as_float(vt[i]) * scale_log2e : -INFINITY;  // keys >= 197 masked
-          mrun = fmaxf(mrun, t[i]);
-        }
-        ref[6] = mrun;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 pk;
-          __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) ph[u] = __floats2half2_rn(t[8 * j + 2 * u] - mrun, t[8 * j + 2 * u + 1] - mrun);
-          *reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4)) = pk;  // SWIZZLE_32B: bit 4 ^= bit 7
-        }
-      }
-      // S fully read: the accumulator columns may be overwritten by P V (which aliases them) once P is ready
-      tcgen05_fence_before();
-      // Pass 2 -- shared memory only (each thread re-reads what it wrote): p = 2^(d + ref[c] - m), row sum, in place
-      float sum;
-      {
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const float off = ref[c] - mrun;
-          uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int piece = (c & 1) * 4 + j;
-            uint4* slot = reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4));
-            uint4 pk = *slot;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 d = __half22float2(ph[u]);
-              const float p0 = ex2_approx(d.x + off), p1 = ex2_approx(d.y + off);
-              s4[(2 * u) & 3] += p0;
-              s4[(2 * u + 1) & 3] += p1;
-              ph[u] = __floats2half2_rn(p0, p1);
-            }
-            *slot = pk;
-          }
-        }
+        // S fully read: the accumulator columns may be overwritten by P V (which aliases them) once P is ready
+        tcgen05_fence_before();
+        // Pass 2 -- shared memory only (each thread re-reads what it wrote): p = 2^(d + ref[c] - m), row sum, in place
         {
-          const float off = ref[6] - mrun;  // == 0
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4* slot = reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4));
-            uint4 pk = *slot;
-            __half2* ph = reinterpret_cast<__half2*>(&pk);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 d = __half22float2(ph[u]);
-              const float p0 = ex2_approx(d.x + off), p1 = ex2_approx(d.y + off);  // 2^-inf = 0 for masked keys
-              s4[(2 * u) & 3] += p0;
-              s4[(2 * u + 1) & 3] += p1;
-              ph[u] = __floats2half2_rn(p0, p1);
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+  #pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const float off = ref[c] - mrun;
+            uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int piece = (c & 1) * 4 + j;
+              uint4* slot = reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4));
+              uint4 pk = *slot;
+              __half2* ph = reinterpret_cast<__half2*>(&pk);
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 d = __half22float2(ph[u]);
+                const float p0 = ex2_approx(d.x + off), p1 = ex2_approx(d.y + off);
+                s4[(2 * u) & 3] += p0;
+                s4[(2 * u + 1) & 3] += p1;
+                ph[u] = __floats2half2_rn(p0, p1);
+              }
+              *slot = pk;
             }
-            *slot = pk;
+          }
+          {
+            const float off = ref[6] - mrun;  // == 0
+  #pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4* slot = reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4));
+              uint4 pk = *slot;
+              __half2* ph = reinterpret_cast<__half2*>(&pk);
+  #pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 d = __half22float2(ph[u]);
+                const float p0 = ex2_approx(d.x + off), p1 = ex2_approx(d.y + off);  // 2^-inf = 0 for masked keys
+                s4[(2 * u) & 3] += p0;
+                s4[(2 * u + 1) & 3] += p1;
+                ph[u] = __floats2half2_rn(p0, p1);
+              }
+              *slot = pk;
+            }
+          }
+          sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+      } else {
+        // pass 1: row maximum over the 197 valid keys (chunk c+1 in flight while chunk c is reduced)
+        float mx;
+        {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains: FMNMX latency, not count
+          uint32_t v[2][32];
+          uint32_t vt[16];
+          tmem_ld_32x32b_x32(trow, v[0]);
+  #pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+            else tmem_ld_32x32b_x16(trow + 192, vt);
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[c & 1][i]));
+          }
+          tmem_ld_wait();
+  #pragma unroll
+          for (int i = 0; i < 5; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(vt[i]));  // keys 192..196
+          mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        }
+        const float moff = mx * scale_log2e;
+        // pass 2: p = 2^(s * scale - max * scale), row sum, P -> smem (fp16, K-major, swizzled)
+        {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t v[2][32];
+          uint32_t vt[16];
+          tmem_ld_32x32b_x32(trow, v[0]);
+  #pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < 6) tmem_ld_32x32b_x32(trow + (c + 1) * 32, v[(c + 1) & 1]);
+            else tmem_ld_32x32b_x16(trow + 192, vt);
+            float p[32];
+  #pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              p[i] = ex2_approx(fmaf(__uint_as_float(v[c & 1][i]), scale_log2e, -moff));
+              s4[i & 3] += p[i];
+            }
+            uint8_t* chunk = pmain + (c >> 1) * kAtQBytes;
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 pk;
+              __half2* ph = reinterpret_cast<__half2*>(&pk);
+  #pragma unroll
+              for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(p[8 * j + 2 * t], p[8 * j + 2 * t + 1]);
+              const int piece = (c & 1) * 4 + j;  // 16-byte piece inside the 64-key chunk
+              *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk;
+            }
+          }
+          tmem_ld_wait();
+          float p[16];
+  #pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            p[i] = (i < 5) ? ex2_approx(fmaf(__uint_as_float(vt[i]), scale_log2e, -moff)) : 0.f;  // keys >= 197 masked
+            s4[i & 3] += p[i];
+          }
+          sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  #pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+  #pragma unroll
+            for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(p[8 * j + 2 * t], p[8 * j + 2 * t + 1]);
+            *reinterpret_cast<uint4*>(ptail + ((j ^ ((r >> 2) & 1)) << 4)) = pk;  // SWIZZLE_32B: bit 4 ^= bit 7
           }
         }
-        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        tcgen05_fence_before();
       }
       // P written: make the generic-proxy writes visible to the MMA (async proxy), then signal
       fence_proxy_async_smem();

@@ -220,9 +220,58 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
   }
 }
 
+// a1 on the device for the no-resize case of EffLocalizer.letterbox (localizer_engine.py:107-138 with r == 1, e.g.
+// 64 x 1024 lines into a 64 x 1024 or larger model shape): place the u8 RGB line at (top, left) of a grey (114) canvas
+// and emit the f32 NCHW tensor of load_localizer_img (:80-85: BGR->RGB, / 255).  Bit-exact: no interpolation happens.
+__global__ void __launch_bounds__(256) letterbox_pad_kernel(const uint8_t* __restrict__ pixels,
+                                                            const effocr_image_desc* __restrict__ images, int n_images,
+                                                            int H, int W, float* __restrict__ out) {
+  const long long total = static_cast<long long>(n_images) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(W) * H));
+    const effocr_image_desc im = images[b];
+    // dw, dh split exactly like the reference: top = round(dh/2 - 0.1), left = round(dw/2 - 0.1)
+    const int dh = H - im.height, dw = W - im.width;
+    const int top = static_cast<int>(rintf(dh * 0.5f - 0.1f)), left = static_cast<int>(rintf(dw * 0.5f - 0.1f));
+    const int sy = y - top, sx = x - left;
+    float r = 114.0f / 255.0f, g = r, bl = r;
+    if (sy >= 0 && sy < im.height && sx >= 0 && sx < im.width) {
+      const uint8_t* p = pixels + im.offset + static_cast<long long>(sy) * im.pitch + sx * 3;
+      r = static_cast<float>(p[0]) / 255.0f;
+      g = static_cast<float>(p[1]) / 255.0f;
+      bl = static_cast<float>(p[2]) / 255.0f;
+    }
+    float* o = out + (static_cast<long long>(b) * 3 * H + y) * W + x;
+    o[0] = r;
+    o[static_cast<long long>(H) * W] = g;
+    o[2LL * H * W] = bl;
+  }
+}
+
 }  // namespace effocr
 
 using namespace effocr;
+
+extern "C" int effocr_letterbox_pad(const uint8_t* d_pixels, const effocr_image_desc* d_images, int n_images, int height,
+                                    int width, float* d_out, void* stream) {
+  EFFOCR_TRY(require_sm100());
+  if (n_images < 0 || height <= 0 || width <= 0) return fail(EFFOCR_ERR_INVALID, "letterbox_pad: bad arguments");
+  if (n_images == 0) return EFFOCR_OK;
+  if (!d_pixels || !d_images || !d_out) return fail(EFFOCR_ERR_INVALID, "letterbox_pad: null buffer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n_images) * height * width;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  {
+    KernelScope ks(PROF_YOLO_MISC, s);
+    letterbox_pad_kernel<<<static_cast<int>(g), 256, 0, s>>>(d_pixels, d_images, n_images, height, width, d_out);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
 
 extern "C" int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
                                   const effocr_crop_box* d_boxes, int n_boxes, int layout, void* d_out, void* stream) {

@@ -83,7 +83,10 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
   return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 
-// impl 0: tcgen05 kernel (attention_sm100.cuh); impl 1: first-generation mma.sync kernel (kept as an A/B reference)
+// impl 0: tcgen05 kernel (attention_sm100.cuh), softmax variant chosen by kAttentionDefaultSinglePass;
+// impl 1: first-generation mma.sync kernel (kept as an A/B reference); impl 2 / 3: tcgen05 kernel with the
+// two-pass / single-pass softmax forced (A/B)
+constexpr bool kAttentionDefaultSinglePass = false;
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
@@ -98,9 +101,15 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
   } else {
     static bool attr = false;
     if (!attr) {
-      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       attr = true;
     }
+    static const int env_variant = [] {
+      const char* e = getenv("EFFOCR_ATTENTION_SOFTMAX");  // "1" = single TMEM pass, "2" = two passes; for A/B runs
+      return e ? atoi(e) : 0;
+    }();
+    const bool single = impl == 3 || (impl == 0 && (env_variant == 1 || (env_variant == 0 && kAttentionDefaultSinglePass)));
     const long long rows = static_cast<long long>(batch) * T;
     const int D = H * 64;
     CUtensorMap tq, tkv;
@@ -109,7 +118,8 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     const int pairs = batch * H;
     const int grid = pairs < sm_count() ? pairs : sm_count();
     KernelScope ks(PROF_ATTENTION, s);
-    attention_tc_kernel<<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    if (single) attention_tc_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    else attention_tc_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

@@ -65,10 +65,17 @@ class EffOCRPipeline:
             self.candidate_chars = [c for c in self.candidate_chars if c not in blacklist]
 
     # -- phase 1: localize a batch of RGB u8 line images
-    def localize(self, images_rgb):
+    def localize(self, images_rgb, packed=None):
         shape = self.localizer._input_shape
-        lb = [EffLocalizer.preprocess_bgr(np.ascontiguousarray(im[:, :, ::-1]), shape) for im in images_rgb]
-        x = torch.from_numpy(np.concatenate(lb, 0)).cuda(non_blocking=True)
+        no_resize = all(min(shape[0] / im.shape[0], shape[1] / im.shape[1]) == 1.0 for im in images_rgb)
+        if no_resize:
+            # r == 1: the reference's letterbox only pads -> done on the device from the u8 pixels (bit-exact)
+            if packed is None:
+                packed = ops.pack_images(images_rgb)
+            x = ops.letterbox_pad(packed[0], packed[1], len(images_rgb), shape[0], shape[1])
+        else:
+            lb = [EffLocalizer.preprocess_bgr(np.ascontiguousarray(im[:, :, ::-1]), shape) for im in images_rgb]
+            x = torch.from_numpy(np.concatenate(lb, 0)).cuda(non_blocking=True)
         out, cnt = self.localizer.run_device(x)
         out, cnt = out.cpu(), cnt.cpu().tolist()
         return [out[i, :cnt[i]] for i in range(len(images_rgb))]
@@ -121,6 +128,19 @@ class EffOCRPipeline:
                 text = textproc.en_postprocess(first, wei, heights, bottoms, anchor_margin=self.anchor_margin)
             results.append({"text": text, "nns": nns, "char_boxes": [b.tolist() for b in char_b], "word_end_idx": wei})
         return results
+
+
+def run_effocr_sharded(images_rgb, pipeline, keys=None, batch_lines: int = 64, weights=None):
+    """Data-parallel driver: every rank transcribes its shard of the lines, rank 0 gets the
+    merged {key: text}.  Results are keyed by input and per-line arithmetic does not depend on batch composition,
+    so the output is independent of the world size."""
+    from . import dist as D
+
+    rank, world, _ = D.init_from_env()
+    keys = list(range(len(images_rgb))) if keys is None else list(keys)
+    mine = D.shard_indices(len(images_rgb), rank, world, weights=weights)
+    local = run_effocr([images_rgb[i] for i in mine], pipeline, batch_lines=batch_lines, keys=[keys[i] for i in mine])
+    return D.gather_results(local)
 
 
 def run_effocr(images_rgb, pipeline: EffOCRPipeline, batch_lines: int = 64, keys=None):

@@ -99,6 +99,16 @@ def crop_resize(pixels: torch.Tensor, images: torch.Tensor, boxes: torch.Tensor,
     return out
 
 
+def letterbox_pad(pixels: torch.Tensor, images: torch.Tensor, n_images: int, height: int, width: int) -> torch.Tensor:
+    """u8 RGB line images (no larger than height x width) -> letterboxed f32 [n, 3, height, width] on the device."""
+    lib = _lib.load()
+    pixels = _cuda(pixels, torch.uint8, "pixels")
+    out = torch.empty((n_images, 3, height, width), device=pixels.device, dtype=torch.float32)
+    _lib.check(lib.effocr_letterbox_pad(pixels.data_ptr(), images.data_ptr(), n_images, height, width, out.data_ptr(),
+                                        _lib.stream_ptr()), "effocr_letterbox_pad")
+    return out
+
+
 def pack_images(arrays, device="cuda", pinned: bool = True):
     """Concatenate u8 HWC RGB images into one device buffer + descriptor table (one H2D copy each)."""
     descs = np.zeros(len(arrays), dtype=IMAGE_DESC_DTYPE)

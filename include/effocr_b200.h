@@ -92,6 +92,14 @@ typedef struct {
 EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
                                   const effocr_crop_box* d_boxes, int n_boxes, int layout, void* d_out, void* stream);
 
+/* ---- a1: letterbox without resize (r == 1) on the device ------------------------------------------
+ * Replaces EffLocalizer.load_localizer_img / letterbox (onnx_engines/localizer_engine.py:75-85,107-138) when the
+ * line image already fits the model shape: pad to (height, width) with grey 114 (top = round(dh/2 - 0.1),
+ * left = round(dw/2 - 0.1)), RGB order, / 255 -> fp32 [n, 3, height, width].  Images larger than the canvas are
+ * not handled here (the resize path stays on the host with OpenCV, like the reference). */
+EFFOCR_API int effocr_letterbox_pad(const uint8_t* d_pixels, const effocr_image_desc* d_images, int n_images, int height,
+                                    int width, float* d_out, void* stream);
+
 /* ---- recognizer encoder: timm vit_{tiny,small,base}_patch16_224, num_classes=0 ----------------
  * Replaces AutoEncoder.forward (models/encoders.py:62-64, called at infer_effocr.py:314) and
  * EffRecognizer.run (onnx_engines/recognizer_engine.py:23-27).

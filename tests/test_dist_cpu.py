@@ -56,3 +56,17 @@ def test_shard_indices_weighted_is_partition_and_balanced():
     # results independent of world size: the union of shards is always the full set
     for world in (1, 2, 3, 8):
         assert sorted(sum((D.shard_indices(len(w), r, world) for r in range(world)), [])) == list(range(len(w)))
+
+
+def test_run_effocr_sharded_single_process_uses_pipeline_contract():
+    """The sharded driver only needs `infer_lines`; with world size 1 it returns every key, sorted."""
+    from effocr_b200.infer import run_effocr_sharded
+
+    class Fake:
+        def infer_lines(self, imgs):
+            return [{"text": f"t{int(im[0, 0, 0])}"} for im in imgs]
+
+    import numpy as np
+    imgs = [np.full((2, 2, 3), i, np.uint8) for i in range(7)]
+    out = run_effocr_sharded(imgs, Fake(), keys=[f"k{i}" for i in range(7)], batch_lines=3)
+    assert out == {f"k{i}": f"t{i}" for i in range(7)}

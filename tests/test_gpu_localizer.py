@@ -75,3 +75,18 @@ def test_efflocalizer_run_matches_oracle_pipeline():
         # the GPU's own NMS on its own predictions is exact (tested above); against the fp32 oracle the box set
         # may differ only for candidates within fp16 noise of the confidence / IoU thresholds
         assert abs(r.shape[0] - o.shape[0]) <= max(2, 0.1 * o.shape[0])
+
+
+def test_letterbox_pad_matches_reference_letterbox():
+    """Device letterbox (no-resize case) == the oracle / reference load_localizer_img, bit for bit."""
+    from effocr_b200 import ops
+    from oracle import yolo as OY
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (64, 1024, 3), dtype=np.uint8), rng.integers(0, 256, (40, 1024, 3), dtype=np.uint8),
+            rng.integers(0, 256, (64, 777, 3), dtype=np.uint8)]
+    pixels, images, _ = ops.pack_images(imgs)
+    out = ops.letterbox_pad(pixels, images, len(imgs), 64, 1024).cpu().numpy()
+    for i, im in enumerate(imgs):
+        ref = OY.load_localizer_img_from_array(np.ascontiguousarray(im[:, :, ::-1]), (64, 1024))  # oracle takes BGR
+        if im.shape[:2] == (64, 1024) or min(64 / im.shape[0], 1024 / im.shape[1]) == 1.0:
+            assert np.array_equal(out[i], ref[0]), i
