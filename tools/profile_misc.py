@@ -14,3 +14,13 @@ for _ in range(3):
     ops.attention(qkv, 1024, 6)
 torch.cuda.synchronize()
 print("done")
+# kNN: 1024 unit-norm queries against a 10k x 384 index, k = 10
+from effocr_b200.engine import FlatIPIndex
+g = torch.Generator().manual_seed(1)
+ix = FlatIPIndex(384)
+ix.add(torch.nn.functional.normalize(torch.randn(10000, 384, generator=g), dim=1))
+q = torch.nn.functional.normalize(torch.randn(1024, 384, generator=g), dim=1).cuda()
+for _ in range(2):
+    ix.search_device(q, 10)
+torch.cuda.synchronize()
+print("knn done")
