@@ -41,6 +41,8 @@ SIGNATURES = {
     "effocr_profile_read": (c_int, [c_int, c_void_p, c_void_p]),
     "effocr_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "effocr_mlp_fused_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
+                                     c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),

@@ -1,0 +1,23 @@
+// Internal C++ interface to the fused MLP block kernel (mlp_sm100.cuh).
+#pragma once
+#include "host_common.h"
+
+namespace effocr {
+
+struct MlpArgs {
+  const __half* h = nullptr;  // [M, D] LayerNorm output, leading dimension ldh
+  long long ldh = 0;
+  const __half* w1 = nullptr;  // [HID, D] fc1 weight (torch Linear layout)
+  const float* b1 = nullptr;   // [HID]
+  const __half* w2 = nullptr;  // [D, HID] fc2 weight
+  const float* b2 = nullptr;   // [D]
+  float* x = nullptr;          // [M, D] fp32 residual stream, updated in place
+  long long ldx = 0;
+  int M = 0, D = 0, HID = 0;
+};
+
+bool mlp_fused_supported(int D, int HID);
+// x += GELU(h . w1^T + b1) . w2^T + b2
+int mlp_fused_f16(const MlpArgs& a, cudaStream_t stream);
+
+}  // namespace effocr

@@ -4,10 +4,13 @@
 //
 // Numerics: fp16 GEMM operands, fp32 accumulation (TMEM), fp32 residual stream, fp32 LayerNorm /
 // softmax statistics -- SURVEY.md section 0.5 (bf16 or an fp16 residual flips top-1 ids).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "../../include/effocr_b200.h"
 #include "gemm.h"
+#include "mlp.h"
 #include "attention_sm100.cuh"
 #include "vit_kernels.cuh"
 
@@ -141,6 +144,11 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     cls_pos_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(v->x, v->cls, v->pos, B, T, D);
   }
   EFFOCR_CUDA(cudaGetLastError());
+  static const bool fused_env = [] {
+    const char* e = getenv("EFFOCR_MLP_FUSED");  // "0" = unfused fc1 / fc2 GEMMs (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  const bool fused_mlp = fused_env && mlp_fused_supported(D, v->mlp);
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
@@ -154,6 +162,13 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
     EFFOCR_TRY(gemm_f16(g, s));
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
+    if (fused_mlp) {  // fc1 + GELU + fc2 + residual in one kernel: the [M, mlp] hidden activations never reach HBM
+      MlpArgs m;
+      m.h = v->h16; m.ldh = D; m.w1 = L.w_fc1; m.b1 = L.b_fc1; m.w2 = L.w_fc2; m.b2 = L.b_fc2;
+      m.x = v->x; m.ldx = D; m.M = M; m.D = D; m.HID = v->mlp;
+      EFFOCR_TRY(mlp_fused_f16(m, s));
+      continue;
+    }
     g = GemmArgs();
     g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = M; g.N = v->mlp; g.K = D;
     g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1; g.prof_tag = PROF_GEMM_FC1;

@@ -49,6 +49,24 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = ACT_NONE, out_d
     return out
 
 
+def mlp_fused(x: torch.Tensor, h: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
+              b2: torch.Tensor) -> torch.Tensor:
+    """x += GELU(h @ w1.T + b1) @ w2.T + b2 in place (fp32 residual x, fp16 h / weights); one fused tcgen05 kernel."""
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x")
+    h = _cuda(h, torch.float16, "h")
+    w1 = _cuda(w1, torch.float16, "w1")
+    w2 = _cuda(w2, torch.float16, "w2")
+    M, D = x.shape
+    HID = w1.shape[0]
+    assert h.shape == (M, D) and w1.shape == (HID, D) and w2.shape == (D, HID) and w1.is_contiguous() and w2.is_contiguous()
+    assert x.stride(1) == 1 and h.stride(1) == 1
+    _lib.check(lib.effocr_mlp_fused_f16(h.data_ptr(), h.stride(0), w1.data_ptr(), _cuda(b1, torch.float32, "b1").data_ptr(),
+                                        w2.data_ptr(), _cuda(b2, torch.float32, "b2").data_ptr(), x.data_ptr(), x.stride(0),
+                                        M, D, HID, _lib.stream_ptr()), "effocr_mlp_fused_f16")
+    return x
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
               out_dtype=torch.float16) -> torch.Tensor:
     lib = _lib.load()

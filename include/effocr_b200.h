@@ -68,6 +68,13 @@ EFFOCR_API int effocr_gemm_f16(const void* d_A, long long lda, const void* d_W, 
                     const float* d_bias, const float* d_gamma, const void* d_resid, long long ldr, void* d_out,
                     long long ldo, int act, int out_f32, int block_n, void* stream);
 
+/* ---- fused transformer MLP block (tcgen05, CTA pairs) -------------------------------------
+ * x[M,D] += GELU(h[M,D] . W1[HID,D]^T + b1) . W2[D,HID]^T + b2     fp16 operands, fp32 accumulate / residual.
+ * The `x = x + mlp(norm2(x))` half of timm Block.forward (un-vendored; reached from models/encoders.py:58,62-64)
+ * after the LayerNorm; the [M,HID] hidden activations stay on chip.  D in {192, 384}, HID % 128 == 0. */
+EFFOCR_API int effocr_mlp_fused_f16(const void* d_h, long long ldh, const void* d_w1, const float* d_b1, const void* d_w2,
+                         const float* d_b2, float* d_x, long long ldx, int M, int D, int HID, void* stream);
+
 /* ---- K1: fused crop -> square white pad -> AA bilinear 224x224 -> normalise -------------------
  * Replaces the numpy slice + `create_paired_transform` per-crop CPU path
  * (infer_effocr.py:284-293, infer_effocr_onnx_multi.py:307-340, utils/datasets_utils.py:69-90,166-172).
