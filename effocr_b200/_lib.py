@@ -45,6 +45,7 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "effocr_letterbox_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_vit_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_int, c_void_p]),
     "effocr_vit_destroy": (None, [c_void_p]),
     "effocr_vit_embed_dim": (c_int, [c_void_p]),

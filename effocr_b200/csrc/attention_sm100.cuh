@@ -144,36 +144,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
     // ---------------- MMA issuer.  Issue order per pair i:  S0(i), PV1(i-1), S1(i), PV0(i)  -- the two query-tile
     // groups run half a period out of phase, so one group's MUFU-bound softmax overlaps the other group's MMAs,
     // TMEM waits and epilogue instead of both groups competing for the MUFU pipe and then idling together.
-    if (elect_one_sync()) {
+    // The whole warp walks the loop (waits and descriptor arithmetic stay warp-uniform, i.e. in uniform registers);
+    // only the tcgen05 instructions are predicated on one elected lane -- issuing from inside an `if (elect_one)`
+    // region costs a R2UR waterfall of ~16 instructions per MMA, three times the 32 cycles an N = 64 MMA runs for.
+    {
+      const bool leader_lane = elect_one_sync();
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
       constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
+      const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
       auto issue_s = [&](int g, int it) {
         const uint32_t par = it & 1;
         const int s = it & 1;
         mbar_wait(&q_full[g], par);
         mbar_wait(&t_free[g], par ^ 1);  // region g (S/O columns) drained by the previous pair's epilogue
         tcgen05_fence_after();
-        const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + g * kAtQBytes));
-        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem_k + s * kAtKVBytes));
+        const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
+        const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
+        if (leader_lane) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
-        umma_commit(&q_empty[g]);
-        umma_commit(&s_full[g]);
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(&q_empty[g]);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int g, int it) {
         const uint32_t par = it & 1;
         mbar_wait(&p_full[g], par);  // all four warps of the group have read S_g and written P_g
         tcgen05_fence_after();
-        const uint32_t pbase = smem_u32(smem_p + g * kAtPBytes);
+        const uint32_t pbase = p_base + g * kAtPBytes;
+        if (leader_lane) {
 #pragma unroll
-        for (int ks = 0; ks < 12; ++ks) {
-          const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
-          const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem_v + ks * 2048));
-          umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+          for (int ks = 0; ks < 12; ++ks) {
+            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+          }
+          umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
+                   make_sw128_mnmajor_desc(v_base + 12 * 2048), idesc_o, 1u);
+          umma_commit(&o_full[g]);
         }
-        umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
-                 make_sw128_mnmajor_desc(smem_u32(smem_v + 12 * 2048)), idesc_o, 1u);
-        umma_commit(&o_full[g]);
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader_lane) umma_commit(bar);
+        __syncwarp();
       };
       int it = 0;
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
@@ -182,16 +197,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
         issue_s(0, it);
         if (it > 0) {
           issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
-          umma_commit(v_empty);
+          commit(v_empty);
         }
         issue_s(1, it);
-        umma_commit(&k_empty[s]);
+        commit(&k_empty[s]);
         mbar_wait(v_full, it & 1);  // V(it), reloaded after PV1(it-1) retired
         issue_pv(0, it);
       }
       if (it > 0) {
         issue_pv(1, it - 1);
-        umma_commit(v_empty);
+        commit(v_empty);
       }
     }
   } else if (warp_idx >= 4) {

@@ -251,9 +251,75 @@ __global__ void __launch_bounds__(256) letterbox_pad_kernel(const uint8_t* __res
   }
 }
 
+// a1 on the device, general case: EffLocalizer.letterbox (localizer_engine.py:107-138) = cv2.resize(INTER_LINEAR) of the
+// u8 line to (nw, nh) followed by grey (114) padding, then load_localizer_img's CHW / RGB / float32 / 255 (:80-85).
+// cv2's 8-bit linear resize is fixed-point and therefore reproducible bit for bit (OpenCV imgproc/resize.cpp,
+// HResizeLinear + VResizeLinear<uchar,int,short>): horizontal taps a0 + a1 = 2048 (11 bits) applied to u8 pixels,
+// vertical taps b0, b1 applied as ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16), then (+2) >> 2.  The tap
+// tables (source index pair + coefficient pair per destination column / row) are built on the host with OpenCV's
+// own float arithmetic (localizer_engine.letterbox_plan) -- a few KB per distinct line shape.
+__global__ void __launch_bounds__(256) letterbox_resize_kernel(const uint8_t* __restrict__ pixels,
+                                                               const effocr_image_desc* __restrict__ images,
+                                                               const effocr_letterbox_plan* __restrict__ plans,
+                                                               const int4* __restrict__ taps, int n_images, int H, int W,
+                                                               float* __restrict__ out) {
+  const long long total = static_cast<long long>(n_images) * H * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % W);
+    const int y = static_cast<int>((i / W) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(W) * H));
+    const effocr_letterbox_plan pl = plans[b];
+    const int dy = y - pl.top, dx = x - pl.left;
+    float r = 114.0f / 255.0f, g = r, bl = r;
+    if (dy >= 0 && dy < pl.new_height && dx >= 0 && dx < pl.new_width) {
+      const effocr_image_desc im = images[b];
+      const int4 tx = __ldg(taps + pl.xtap_offset + dx);  // (sx0, sx1, a0, a1)
+      const int4 ty = __ldg(taps + pl.ytap_offset + dy);  // (sy0, sy1, b0, b1)
+      const uint8_t* r0 = pixels + im.offset + static_cast<long long>(ty.x) * im.pitch;
+      const uint8_t* r1 = pixels + im.offset + static_cast<long long>(ty.y) * im.pitch;
+      int v[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int s0 = r0[tx.x * 3 + c] * tx.z + r0[tx.y * 3 + c] * tx.w;
+        const int s1 = r1[tx.x * 3 + c] * tx.z + r1[tx.y * 3 + c] * tx.w;
+        int o = (((ty.z * (s0 >> 4)) >> 16) + ((ty.w * (s1 >> 4)) >> 16) + 2) >> 2;
+        v[c] = o < 0 ? 0 : (o > 255 ? 255 : o);
+      }
+      r = __fdiv_rn(static_cast<float>(v[0]), 255.0f);
+      g = __fdiv_rn(static_cast<float>(v[1]), 255.0f);
+      bl = __fdiv_rn(static_cast<float>(v[2]), 255.0f);
+    }
+    float* o = out + (static_cast<long long>(b) * 3 * H + y) * W + x;
+    o[0] = r;
+    o[static_cast<long long>(H) * W] = g;
+    o[2LL * H * W] = bl;
+  }
+}
+
 }  // namespace effocr
 
 using namespace effocr;
+
+extern "C" int effocr_letterbox_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
+                                       const effocr_letterbox_plan* d_plans, const void* d_taps, int n_images, int height,
+                                       int width, float* d_out, void* stream) {
+  EFFOCR_TRY(require_sm100());
+  if (n_images < 0 || height <= 0 || width <= 0) return fail(EFFOCR_ERR_INVALID, "letterbox_resize: bad arguments");
+  if (n_images == 0) return EFFOCR_OK;
+  if (!d_pixels || !d_images || !d_plans || !d_taps || !d_out) return fail(EFFOCR_ERR_INVALID, "letterbox_resize: null buffer");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(n_images) * height * width;
+  long long g = (total + 255) / 256;
+  if (g > 148 * 32) g = 148 * 32;
+  {
+    KernelScope ks(PROF_YOLO_MISC, s);
+    letterbox_resize_kernel<<<static_cast<int>(g), 256, 0, s>>>(d_pixels, d_images, d_plans, reinterpret_cast<const int4*>(d_taps),
+                                                                 n_images, height, width, d_out);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
 
 extern "C" int effocr_letterbox_pad(const uint8_t* d_pixels, const effocr_image_desc* d_images, int n_images, int height,
                                     int width, float* d_out, void* stream) {

@@ -356,30 +356,37 @@ gemm_tn_tma_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_const
       }
     }
   } else if (warp_idx == 1) {
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // The whole warp walks the loop so waits and descriptor arithmetic stay warp-uniform (uniform registers); only the
+    // tcgen05 instructions are predicated on one elected lane.  Issuing from inside an `if (elect_one)` region costs
+    // a R2UR waterfall of ~16 instructions per MMA (see mlp_sm100.cuh).
+    const bool leader_lane = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+        const uint64_t da = make_sw128_kmajor_desc(a_base + stage * Cfg::kABytes);
+        const uint64_t db = make_sw128_kmajor_desc(b_base + stage * Cfg::kBBytes);
+        if (leader_lane) {
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k)
             umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (leader_lane) umma_commit(&tfull_bar[as]);
+      __syncwarp();
     }
   } else if (warp_idx >= 4) {
     // Each epilogue warp owns a 32-row band (its TMEM lane quarter q) of one column half and works
@@ -499,34 +506,38 @@ gemm_tn_astat_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_con
       }
     }
   } else if (warp_idx == 1) {
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t a_phase = 0;
-      int local = 0;
-      for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x, a_phase ^= 1) {
-        for (int nb = 0; nb < num_n; ++nb, ++local) {
-          const int as = local & 1;
-          const uint32_t aphase = (local >> 1) & 1;
-          mbar_wait(&tempty_bar[as], aphase ^ 1);
+    const bool leader_lane = elect_one_sync();  // warp-uniform loop, predicated tcgen05 issue (see gemm_tn_tma_kernel)
+    constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t a_phase = 0;
+    int local = 0;
+    for (int mb = blockIdx.x; mb < num_m; mb += gridDim.x, a_phase ^= 1) {
+      for (int nb = 0; nb < num_n; ++nb, ++local) {
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (nb == 0) mbar_wait(&afull_bar[kb], a_phase);
+          mbar_wait(&bfull_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            if (nb == 0) mbar_wait(&afull_bar[kb], a_phase);
-            mbar_wait(&bfull_bar[stage], phase);
-            tcgen05_fence_after();
-            const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + kb * Cfg::kABytes));
-            const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t da = make_sw128_kmajor_desc(a_base + kb * Cfg::kABytes);
+          const uint64_t db = make_sw128_kmajor_desc(b_base + stage * Cfg::kBBytes);
+          if (leader_lane) {
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
             umma_commit(&bempty_bar[stage]);
             if (nb == num_n - 1) umma_commit(&aempty_bar[kb]);  // A k-block free for the next row block
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
-          umma_commit(&tfull_bar[as]);
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        if (leader_lane) umma_commit(&tfull_bar[as]);
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4 && EPI_WARPS == 16) {
@@ -659,8 +670,10 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       }
     }
   } else if (warp_idx == 1) {
-    if (rank == 0 && elect_one_sync()) {
+    if (rank == 0) {
+      const bool leader_lane = elect_one_sync();  // warp-uniform loop, predicated tcgen05 issue (see gemm_tn_tma_kernel)
       constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, BLOCK_N);
+      const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -673,15 +686,19 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+          const uint64_t da = make_sw128_kmajor_desc(a_base + stage * Cfg::kABytes);
+          const uint64_t db = make_sw128_kmajor_desc(b_base + stage * Cfg::kBBytes);
+          if (leader_lane) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k)
-            umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage]);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tfull_bar[as]);
+        if (leader_lane) umma_commit_2sm(&tfull_bar[as]);
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4) {

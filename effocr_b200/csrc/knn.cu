@@ -135,29 +135,34 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
       }
     }
   } else if (warp_idx == 1) {
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_f16(kKnnBM, kKnnBN);
-      int stage = 0; uint32_t phase = 0; int local = 0;
-      for (int nt = nt0; nt < nt1; ++nt, ++local) {
-        const int as = local & 1;
-        const uint32_t aphase = (local >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+    // warp-uniform loop, tcgen05 issue predicated on one elected lane (descriptors stay in uniform registers)
+    const bool leader_lane = elect_one_sync();
+    constexpr uint32_t idesc = make_idesc_f16(kKnnBM, kKnnBN);
+    const uint32_t a_base = smem_u32(smem_a), b_base = smem_u32(smem_b);
+    int stage = 0; uint32_t phase = 0; int local = 0;
+    for (int nt = nt0; nt < nt1; ++nt, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kKnnBM * kKnnBK * 2));
-          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * kKnnBN * kKnnBK * 2));
-          const bool second = kb >= kb1;
-          const uint32_t tmem_d = tmem_base + as * 256 + (second ? 128 : 0);
-          const int kk = second ? kb - kb1 : kb;
+        const uint64_t da = make_sw128_kmajor_desc(a_base + stage * kKnnBM * kKnnBK * 2);
+        const uint64_t db = make_sw128_kmajor_desc(b_base + stage * kKnnBN * kKnnBK * 2);
+        const bool second = kb >= kb1;
+        const uint32_t tmem_d = tmem_base + as * 256 + (second ? 128 : 0);
+        const int kk = second ? kb - kb1 : kb;
+        if (leader_lane) {
 #pragma unroll
           for (int k = 0; k < kKnnBK / 16; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kk | k) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == kKnnStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);
+        __syncwarp();
+        if (++stage == kKnnStages) { stage = 0; phase ^= 1; }
       }
+      if (leader_lane) umma_commit(&tfull_bar[as]);
+      __syncwarp();
     }
   } else if (warp_idx >= 4) {
     const int q = warp_idx & 3;

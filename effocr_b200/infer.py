@@ -36,6 +36,22 @@ def crop_rect_onnx_path(bbox, im_height: int, im_width: int, vertical: bool):
     return int(round(x0.item() * im_width / 640)), 0, int(round(x1.item() * im_width / 640)), im_height
 
 
+def crop_rects_onnx_path(bboxes, im_height: int, im_width: int, vertical: bool):
+    """crop_rect_onnx_path for all boxes of a line at once: np.rint on float32 == torch.round (half to even), the
+    rescale in float64 in the reference's operation order ((x * extent) / 640), np.rint == Python round()."""
+    if len(bboxes) == 0:
+        return []
+    b = bboxes.numpy() if isinstance(bboxes, torch.Tensor) else np.asarray([np.asarray(v, dtype=np.float32) for v in bboxes])
+    r = np.rint(b[:, :4].astype(np.float32)).astype(np.float64)
+    if vertical:
+        y0 = np.rint(r[:, 1] * im_height / 640).astype(np.int64)
+        y1 = np.rint(r[:, 3] * im_height / 640).astype(np.int64)
+        return [(0, int(a), im_width, int(c)) for a, c in zip(y0, y1)]
+    x0 = np.rint(r[:, 0] * im_width / 640).astype(np.int64)
+    x1 = np.rint(r[:, 2] * im_width / 640).astype(np.int64)
+    return [(int(a), 0, int(c), im_height) for a, c in zip(x0, x1)]
+
+
 def crop_rect_torch_path(bbox, im_height: int, im_width: int, vertical: bool, double_clipped: bool = True):
     """infer_effocr.py:286-291: int(round(.)) (banker's) on all four coordinates, then double clipping."""
     x0, y0, x1, y1 = map(int, map(round, (float(v) for v in bbox[:4])))
@@ -66,22 +82,22 @@ class EffOCRPipeline:
 
     # -- phase 1: localize a batch of RGB u8 line images
     def localize(self, images_rgb, packed=None):
+        """The u8 lines go to the device once (`packed` = ops.pack_images result, shared with the crop kernel); the
+        reference's letterbox (cv2 resize + pad + /255) runs there bit-exactly, so neither the 4.9 MB float tensor
+        per line nor the OpenCV call is on the host path."""
         shape = self.localizer._input_shape
-        no_resize = all(min(shape[0] / im.shape[0], shape[1] / im.shape[1]) == 1.0 for im in images_rgb)
-        if no_resize:
-            # r == 1: the reference's letterbox only pads -> done on the device from the u8 pixels (bit-exact)
-            if packed is None:
-                packed = ops.pack_images(images_rgb)
-            x = ops.letterbox_pad(packed[0], packed[1], len(images_rgb), shape[0], shape[1])
-        else:
-            lb = [EffLocalizer.preprocess_bgr(np.ascontiguousarray(im[:, :, ::-1]), shape) for im in images_rgb]
-            x = torch.from_numpy(np.concatenate(lb, 0)).cuda(non_blocking=True)
+        if packed is None:
+            packed = ops.pack_images(images_rgb)
+        x = ops.letterbox_resize(packed[0], packed[1], [im.shape[:2] for im in images_rgb], shape[0], shape[1])
         out, cnt = self.localizer.run_device(x)
         out, cnt = out.cpu(), cnt.cpu().tolist()
         return [out[i, :cnt[i]] for i in range(len(images_rgb))]
 
     # -- host logic between the two GPU phases (reference semantics, ONNX path)
     def _boxes_for_line(self, result, im_h, im_w):
+        # numpy float32 rows: the same float32 arithmetic / comparisons as the reference's torch rows, without a
+        # ~5 us torch dispatch per scalar operation (the O(n w) word-end search is ~500 scalar ops per line)
+        result = np.asarray(result, dtype=np.float32)
         bboxes, labels = result[:, :4], result[:, -1]
         word_end_idx = []
         if self.lang == "en":
@@ -92,7 +108,7 @@ class EffOCRPipeline:
             char_b = bboxes[labels == 0]
             if len(char_b) != 0:
                 char_b = textproc.jp_preprocess(char_b, vertical=self.vertical)
-        rects = [crop_rect_onnx_path(b, im_h, im_w, self.vertical) for b in char_b]
+        rects = crop_rects_onnx_path(char_b, im_h, im_w, self.vertical)
         heights = [b[3] - b[1] for b in char_b]
         bottoms = [b[3] for b in char_b]
         return list(char_b), word_end_idx, rects, heights, bottoms
@@ -101,7 +117,8 @@ class EffOCRPipeline:
         """images_rgb: list of u8 [H, W, 3] arrays -> list of dicts (text, nns, char_boxes, word_end_idx)."""
         if len(images_rgb) == 0:
             return []
-        dets = self.localize(images_rgb)
+        packed_images = ops.pack_images(images_rgb)  # ONE upload of the u8 lines for both GPU phases
+        dets = self.localize(images_rgb, packed_images)
         per_line, all_rects = [], []
         for li, (im, det) in enumerate(zip(images_rgb, dets)):
             h, w = im.shape[:2]
@@ -110,8 +127,9 @@ class EffOCRPipeline:
             all_rects += [(li,) + r for r in rects]
         results = []
         if all_rects:
-            packed = PackedCrops(images_rgb, all_rects)
-            dist, idx = self.recognizer.recognize_packed(packed, self.knn)
+            boxes, n = ops.pack_boxes(all_rects)
+            dist, idx, _ = self.recognizer.recognize_device(packed_images[0], packed_images[1], boxes, n, self.knn)
+            idx = idx.cpu().numpy()
         pos = 0
         for (char_b, wei, heights, bottoms, n) in per_line:
             if n == 0:

@@ -60,6 +60,65 @@ def _load_state(model):
     return sd
 
 
+LETTERBOX_PLAN_DTYPE = np.dtype([("new_width", "<i4"), ("new_height", "<i4"), ("left", "<i4"), ("top", "<i4"),
+                                 ("xtap_offset", "<i4"), ("ytap_offset", "<i4")])
+_tap_cache: dict = {}
+
+
+def _resize_taps(src: int, dst: int, clamp_fraction: bool) -> np.ndarray:
+    """Tap table of cv2.resize(INTER_LINEAR) on 8-bit images along one axis: int32 [dst, 4] =
+    (source index 0, source index 1, coefficient 0, coefficient 1), coefficients in 1/2048 units.
+    Follows OpenCV imgproc/resize.cpp: position `(float)((d + 0.5) * scale - 0.5)` with `scale = 1 / (dst / src)` in
+    double, `cvFloor`, coefficients `saturate_cast<short>(f * 2048)` (round half to even).  Along x the fraction is
+    zeroed where the 2-tap window leaves the image (`clamp_fraction`); along y OpenCV keeps the fraction and clips
+    the two row indices instead -- the fixed-point results differ, so both rules are reproduced."""
+    key = (src, dst, clamp_fraction)
+    hit = _tap_cache.get(key)
+    if hit is not None:
+        return hit
+    scale = 1.0 / (float(dst) / float(src))
+    f = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    if clamp_fraction:
+        lo, hi = s < 0, s >= src - 1
+        f[lo | hi] = 0
+        s[lo] = 0
+        s[hi] = src - 1
+    taps = np.empty((dst, 4), dtype=np.int32)
+    taps[:, 0] = np.clip(s, 0, src - 1)
+    taps[:, 1] = np.clip(s + 1, 0, src - 1)
+    taps[:, 2] = np.clip(np.rint((np.float32(1.0) - f) * np.float32(2048.0)), -32768, 32767).astype(np.int32)
+    taps[:, 3] = np.clip(np.rint(f * np.float32(2048.0)), -32768, 32767).astype(np.int32)
+    _tap_cache[key] = taps
+    return taps
+
+
+def letterbox_geometry(height: int, width: int, new_shape=(640, 640)):
+    """localizer_engine.py:107-138 with auto=False, scaleFill=False, scaleup=True: -> (new_width, new_height, left, top)."""
+    r = min(new_shape[0] / height, new_shape[1] / width)
+    nw, nh = int(round(width * r)), int(round(height * r))
+    dw, dh = (new_shape[1] - nw) / 2, (new_shape[0] - nh) / 2
+    return nw, nh, int(round(dw - 0.1)), int(round(dh - 0.1))
+
+
+def letterbox_plan(shapes, new_shape=(640, 640)):
+    """Per-image plans + the concatenated tap tables for effocr_letterbox_resize.  shapes: iterable of (height, width)."""
+    plans = np.zeros(len(shapes), dtype=LETTERBOX_PLAN_DTYPE)
+    tables, offsets, off = [], {}, 0
+    for i, (h, w) in enumerate(shapes):
+        nw, nh, left, top = letterbox_geometry(h, w, new_shape)
+        if nw < 1 or nh < 1:
+            raise _lib.EffocrError(f"letterbox: image {h}x{w} collapses to {nh}x{nw} at model shape {tuple(new_shape)}")
+        for key in ((w, nw, True), (h, nh, False)):
+            if key not in offsets:
+                offsets[key] = off
+                tables.append(_resize_taps(*key))
+                off += key[1]
+        plans[i] = (nw, nh, left, top, offsets[(w, nw, True)], offsets[(h, nh, False)])
+    return plans, np.ascontiguousarray(np.concatenate(tables, 0))
+
+
 class YoloEngine:
     """Device-resident YOLOv5s (fp16 NHWC activations, folded BN) behind effocr_yolo_*."""
 

@@ -127,6 +127,24 @@ def letterbox_pad(pixels: torch.Tensor, images: torch.Tensor, n_images: int, hei
     return out
 
 
+def letterbox_resize(pixels: torch.Tensor, images: torch.Tensor, shapes, height: int, width: int) -> torch.Tensor:
+    """u8 RGB line images of any size -> the reference's letterboxed model input, f32 [n, 3, height, width], on the
+    device: cv2.resize(INTER_LINEAR) restated bit-exactly + grey padding + / 255 (EffLocalizer.load_localizer_img).
+    shapes: [(h, w)] of the packed images (host side, for the tap tables)."""
+    from .localizer_engine import letterbox_plan
+
+    lib = _lib.load()
+    pixels = _cuda(pixels, torch.uint8, "pixels")
+    plans, taps = letterbox_plan(list(shapes), (height, width))
+    d_plans = torch.from_numpy(plans.view(np.uint8).copy()).to(pixels.device, non_blocking=True)
+    d_taps = torch.from_numpy(taps).to(pixels.device, non_blocking=True)
+    out = torch.empty((len(plans), 3, height, width), device=pixels.device, dtype=torch.float32)
+    _lib.check(lib.effocr_letterbox_resize(pixels.data_ptr(), images.data_ptr(), d_plans.data_ptr(), d_taps.data_ptr(),
+                                           len(plans), height, width, out.data_ptr(), _lib.stream_ptr()),
+               "effocr_letterbox_resize")
+    return out
+
+
 def pack_images(arrays, device="cuda", pinned: bool = True):
     """Concatenate u8 HWC RGB images into one device buffer + descriptor table (one H2D copy each)."""
     descs = np.zeros(len(arrays), dtype=IMAGE_DESC_DTYPE)

@@ -110,3 +110,67 @@ def glyph_image(index: int, size: int = 64) -> np.ndarray:
 
 def glyph_images(n: int, size: int = 64):
     return [glyph_image(i, size) for i in range(n)]
+
+
+def random_yolov5s_state_dict(nc: int = 2, seed: int = 0, obj_bias: float | None = None, char_bias: float = 2.0):
+    """Random-init YOLOv5s (ultralytics `model.{i}...` keys; width 0.50 / depth 0.33) for benchmarks and smoke
+    runs -- there is no network for checkpoints.  Kaiming-uniform convolutions, near-identity BatchNorm statistics,
+    Detect biases a la ultralytics (`obj <- log(8 / (640 / s)^2)` unless `obj_bias` is given); `char_bias` is added to
+    the class-0 (character) logit so that, as with a trained EffOCR localizer, most surviving boxes are characters."""
+    import math
+
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(prefix, c1, c2, k):
+        bound = math.sqrt(3.0 / (c1 * k * k))
+        sd[prefix + "conv.weight"] = (torch.rand(c2, c1, k, k, generator=g) * 2 - 1) * bound
+        sd[prefix + "bn.weight"] = 1.0 + 0.1 * torch.randn(c2, generator=g)
+        sd[prefix + "bn.bias"] = 0.1 * torch.randn(c2, generator=g)
+        sd[prefix + "bn.running_mean"] = 0.1 * torch.randn(c2, generator=g)
+        sd[prefix + "bn.running_var"] = 1.0 + 0.2 * torch.rand(c2, generator=g)
+
+    def c3(i, c1, c2, n):
+        p, c_ = f"model.{i}.", c2 // 2
+        conv(p + "cv1.", c1, c_, 1)
+        conv(p + "cv2.", c1, c_, 1)
+        conv(p + "cv3.", 2 * c_, c2, 1)
+        for j in range(n):
+            conv(p + f"m.{j}.cv1.", c_, c_, 1)
+            conv(p + f"m.{j}.cv2.", c_, c_, 3)
+
+    conv("model.0.", 3, 32, 6)
+    conv("model.1.", 32, 64, 3)
+    c3(2, 64, 64, 1)
+    conv("model.3.", 64, 128, 3)
+    c3(4, 128, 128, 2)
+    conv("model.5.", 128, 256, 3)
+    c3(6, 256, 256, 3)
+    conv("model.7.", 256, 512, 3)
+    c3(8, 512, 512, 1)
+    conv("model.9.cv1.", 512, 256, 1)
+    conv("model.9.cv2.", 1024, 512, 1)
+    conv("model.10.", 512, 256, 1)
+    c3(13, 512, 256, 1)
+    conv("model.14.", 256, 128, 1)
+    c3(17, 256, 128, 1)
+    conv("model.18.", 128, 128, 3)
+    c3(20, 256, 256, 1)
+    conv("model.21.", 256, 256, 3)
+    c3(23, 512, 512, 1)
+    no = 5 + nc
+    strides = (8, 16, 32)
+    for l, (c, s) in enumerate(zip((128, 256, 512), strides)):
+        bound = 1.0 / math.sqrt(c)
+        sd[f"model.24.m.{l}.weight"] = (torch.rand(3 * no, c, 1, 1, generator=g) * 2 - 1) * bound
+        b = ((torch.rand(3 * no, generator=g) * 2 - 1) * bound).view(3, no)
+        b[:, 4] += math.log(8 / (640 / s) ** 2) if obj_bias is None else obj_bias
+        b[:, 5:] += math.log(0.6 / (nc - 0.99999))
+        b[:, 5] += char_bias
+        sd[f"model.24.m.{l}.bias"] = b.reshape(-1)
+    anchors = torch.tensor((((10, 13), (16, 30), (33, 23)), ((30, 61), (62, 45), (59, 119)), ((116, 90), (156, 198), (373, 326))),
+                           dtype=torch.float32)
+    sd["model.24.anchors"] = anchors / torch.tensor(strides, dtype=torch.float32).view(3, 1, 1)
+    return sd

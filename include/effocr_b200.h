@@ -107,6 +107,21 @@ EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_de
 EFFOCR_API int effocr_letterbox_pad(const uint8_t* d_pixels, const effocr_image_desc* d_images, int n_images, int height,
                                     int width, float* d_out, void* stream);
 
+/* ---- a1: full letterbox (resize + pad) on the device ------------------------------------------------
+ * Replaces EffLocalizer.load_localizer_img / letterbox (onnx_engines/localizer_engine.py:75-85,107-138) for any line
+ * shape: cv2.resize(INTER_LINEAR) on u8 restated in its own fixed-point arithmetic (bit-exact), grey-114 padding,
+ * RGB order, / 255 -> fp32 [n, 3, height, width].  One plan per image; taps = int32 quadruples
+ * (source index 0, source index 1, coefficient 0, coefficient 1), coefficients scaled by 2048, built on the host by
+ * effocr_b200.localizer_engine.letterbox_plan with OpenCV's float arithmetic. */
+typedef struct effocr_letterbox_plan {
+  int32_t new_width, new_height; /* size after the resize (cv2 `new_unpad`) */
+  int32_t left, top;             /* padding before the content */
+  int32_t xtap_offset, ytap_offset; /* first tap of this image's column / row table inside d_taps (in quadruples) */
+} effocr_letterbox_plan;
+EFFOCR_API int effocr_letterbox_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
+                                       const effocr_letterbox_plan* d_plans, const void* d_taps, int n_images, int height,
+                                       int width, float* d_out, void* stream);
+
 /* ---- recognizer encoder: timm vit_{tiny,small,base}_patch16_224, num_classes=0 ----------------
  * Replaces AutoEncoder.forward (models/encoders.py:62-64, called at infer_effocr.py:314) and
  * EffRecognizer.run (onnx_engines/recognizer_engine.py:23-27).

@@ -187,6 +187,47 @@ def load_localizer_img_from_array(im_bgr: np.ndarray, input_shape=(640, 640)) ->
     return im[None]
 
 
+def cv2_resize_linear_u8(img: np.ndarray, new_w: int, new_h: int) -> np.ndarray:
+    """cv2.resize(img, (new_w, new_h), interpolation=cv2.INTER_LINEAR) for 8-bit images, restated in OpenCV's own
+    fixed-point arithmetic (OpenCV 4.x imgproc/resize.cpp: resizeGeneric_ tap computation, HResizeLinear,
+    VResizeLinear<uchar,int,short> with FixedPtCast<int,uchar,22>) -- the third-party call the reference's letterbox
+    makes (localizer_engine.py:125).  Pinned against live cv2 in tests/test_oracle.py; this is what the device
+    letterbox kernel (csrc/crop.cu letterbox_resize_kernel) must equal bit for bit."""
+    h, w = img.shape[:2]
+
+    def taps(src, dst, clamp_fraction):
+        scale = 1.0 / (float(dst) / float(src))
+        f = ((np.arange(dst, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        s = np.floor(f).astype(np.int64)
+        f = (f - s.astype(np.float32)).astype(np.float32)
+        if clamp_fraction:  # x: fraction zeroed where the window leaves the image; y: rows are clipped instead
+            f[(s < 0) | (s >= src - 1)] = 0
+        i0, i1 = np.clip(s, 0, src - 1), np.clip(s + 1, 0, src - 1)
+        if clamp_fraction:
+            i0 = np.where(s >= src - 1, src - 1, i0)
+        c0 = np.clip(np.rint((np.float32(1) - f) * np.float32(2048)), -32768, 32767).astype(np.int64)
+        c1 = np.clip(np.rint(f * np.float32(2048)), -32768, 32767).astype(np.int64)
+        return i0, i1, c0, c1
+
+    x0, x1, a0, a1 = taps(w, new_w, True)
+    y0, y1, b0, b1 = taps(h, new_h, False)
+    src = img.astype(np.int64)
+    rows0 = src[y0][:, x0] * a0[None, :, None] + src[y0][:, x1] * a1[None, :, None]
+    rows1 = src[y1][:, x0] * a0[None, :, None] + src[y1][:, x1] * a1[None, :, None]
+    out = (((b0[:, None, None] * (rows0 >> 4)) >> 16) + ((b1[:, None, None] * (rows1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def load_localizer_img_restated(im_bgr: np.ndarray, input_shape=(640, 640)) -> np.ndarray:
+    """load_localizer_img_from_array with cv2.resize replaced by cv2_resize_linear_u8 (no OpenCV call at all)."""
+    h, w = im_bgr.shape[:2]
+    _r, new_unpad, top, _bottom, left, _right = letterbox_geometry(h, w, input_shape)
+    im = im_bgr if (w, h) == new_unpad else cv2_resize_linear_u8(im_bgr, new_unpad[0], new_unpad[1])
+    canvas = np.full((input_shape[0], input_shape[1], 3), 114, dtype=np.uint8)
+    canvas[top:top + im.shape[0], left:left + im.shape[1]] = im
+    return (np.ascontiguousarray(canvas.transpose((2, 0, 1))[::-1]).astype(np.float32) / 255.0)[None]
+
+
 # ------------------------------------------------------------------ NMS (localizer_engine.py:171-277)
 def nms_greedy(boxes: torch.Tensor, scores: torch.Tensor, iou_thres: float) -> torch.Tensor:
     """torchvision.ops.nms semantics (its CPU kernel, fp32 op for op): visit boxes by descending score (ties:

@@ -90,3 +90,21 @@ def test_letterbox_pad_matches_reference_letterbox():
         ref = OY.load_localizer_img_from_array(np.ascontiguousarray(im[:, :, ::-1]), (64, 1024))  # oracle takes BGR
         if im.shape[:2] == (64, 1024) or min(64 / im.shape[0], 1024 / im.shape[1]) == 1.0:
             assert np.array_equal(out[i], ref[0]), i
+
+
+@pytest.mark.parametrize("shape", [(640, 640), (64, 1024), (320, 960)])
+def test_letterbox_resize_matches_reference_letterbox(shape):
+    """Device letterbox with resize (cv2.resize INTER_LINEAR restated in fixed point + pad + /255) == the reference's
+    load_localizer_img through live OpenCV, bit for bit, for down-scaled, up-scaled, tall, tiny and exact-fit lines
+    in ONE mixed batch."""
+    from effocr_b200 import ops
+    from oracle import yolo as OY
+    rng = np.random.default_rng(0)
+    hw = [(64, 1024), (64, 1000), (30, 500), (700, 90), (100, 100), (48, 333), (1, 10), (640, 640), (123, 457), (800, 1200),
+          (64, 64), (33, 977), (2, 3)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in hw]
+    pixels, images, _ = ops.pack_images(imgs)
+    out = ops.letterbox_resize(pixels, images, [im.shape[:2] for im in imgs], shape[0], shape[1]).cpu().numpy()
+    for i, im in enumerate(imgs):
+        ref = OY.load_localizer_img_from_array(np.ascontiguousarray(im[:, :, ::-1]), shape)  # oracle takes BGR
+        assert np.array_equal(out[i], ref[0]), (i, im.shape)

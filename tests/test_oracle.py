@@ -108,6 +108,47 @@ def test_letterbox_matches_golden():
         assert int(u8.astype(np.int64).sum()) == int(g[f"sum_{i}"])
 
 
+LETTERBOX_SHAPES = [(64, 1024), (64, 1000), (30, 500), (700, 90), (100, 100), (48, 333), (1, 10), (640, 640), (123, 457),
+                    (800, 1200), (64, 64), (33, 977), (2, 3)]
+
+
+def test_cv2_resize_restatement_matches_live_cv2_and_golden():
+    """The fixed-point restatement of cv2.resize(INTER_LINEAR, u8) equals live OpenCV bit for bit (down- and
+    up-scaling, both edge rules), and the OpenCV-free letterbox equals the reference-generated golden fixtures."""
+    import cv2
+    rng = np.random.default_rng(0)
+    for (h, w) in LETTERBOX_SHAPES:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        for (nw, nh) in [(max(1, w * 5 // 8), max(1, h * 5 // 8)), (w * 2 + 1, h * 3), (640, max(1, round(h * 640 / w)))]:
+            assert np.array_equal(OY.cv2_resize_linear_u8(img, nw, nh), cv2.resize(img, (nw, nh), interpolation=cv2.INTER_LINEAR))
+    g = np.load(GOLDEN / "letterbox_golden.npz")
+    for i, im in enumerate(MG.letterbox_inputs()):
+        x = OY.load_localizer_img_restated(im)
+        assert np.array_equal(x, OY.load_localizer_img_from_array(im))
+        u8 = np.rint(x[0][::-1].transpose(1, 2, 0) * 255).astype(np.uint8)
+        assert np.array_equal(u8[::9, ::9], g[f"sub_{i}"]) and int(u8.astype(np.int64).sum()) == int(g[f"sum_{i}"])
+
+
+def test_letterbox_plan_tables_match_oracle():
+    """Product host logic (localizer_engine.letterbox_plan: geometry + tap tables the device kernel consumes),
+    emulated in numpy, equals the oracle letterbox for every shape."""
+    from effocr_b200.localizer_engine import letterbox_plan
+    rng = np.random.default_rng(1)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in LETTERBOX_SHAPES]
+    plans, taps = letterbox_plan([im.shape[:2] for im in imgs], (640, 640))
+    for im, pl in zip(imgs, plans):
+        tx = taps[pl["xtap_offset"]:pl["xtap_offset"] + pl["new_width"]].astype(np.int64)
+        ty = taps[pl["ytap_offset"]:pl["ytap_offset"] + pl["new_height"]].astype(np.int64)
+        src = im.astype(np.int64)
+        s0 = src[ty[:, 0]][:, tx[:, 0]] * tx[None, :, 2, None] + src[ty[:, 0]][:, tx[:, 1]] * tx[None, :, 3, None]
+        s1 = src[ty[:, 1]][:, tx[:, 0]] * tx[None, :, 2, None] + src[ty[:, 1]][:, tx[:, 1]] * tx[None, :, 3, None]
+        o = (((ty[:, 2, None, None] * (s0 >> 4)) >> 16) + ((ty[:, 3, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+        canvas = np.full((640, 640, 3), 114, np.uint8)
+        canvas[pl["top"]:pl["top"] + pl["new_height"], pl["left"]:pl["left"] + pl["new_width"]] = np.clip(o, 0, 255)
+        got = (canvas.transpose(2, 0, 1).astype(np.float32) / 255.0)[None]
+        assert np.array_equal(got, OY.load_localizer_img_from_array(np.ascontiguousarray(im[:, :, ::-1])))
+
+
 def test_yolov5s_analytic_invariants():
     assert OY.count_parameters(OY.init_yolov5s_state_dict(nc=80)) == 7_235_389  # ultralytics yolov5s
     sd = OY.init_yolov5s_state_dict(nc=2)
