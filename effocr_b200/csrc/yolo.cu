@@ -11,6 +11,8 @@
 // weights / fp32 bias on the host at create time.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include <vector>
 
 #include "../../include/effocr_b200.h"
@@ -48,26 +50,151 @@ __global__ void __launch_bounds__(256) yolo_im2col0_kernel(const float* __restri
   }
 }
 
-// 3x3, pad 1, stride s: NHWC fp16 (pixel pitch ld_in) -> [B*Ho*Wo, 9*C], column = (ky*3 + kx)*C + c
+// ------------------------------------------------------------------ layer 0 as an implicit GEMM (no im2col buffer)
+// Conv(3, 32, k6, s2, p2) + folded BN + SiLU straight from the f32 NCHW image to the fp16 NHWC activation.  With K = 108
+// the explicit im2col matrix is 1.47 GB per 64 lines (written, then read back by the GEMM): 2.3 ms of the 8.5 ms forward.
+// Here a CTA stages the (2*8+4) x (2*32+4) x 3 input patch of an 8 x 32 output tile in shared memory as fp16 and each
+// warp computes one output row (32 pixels x 32 channels) with mma.sync.m16n8k16: the A fragment of k = c*36 + ky*6 + kx
+// is ONE 32-bit shared load (two horizontally adjacent pixels: kx is even), the 32 x 112 weight matrix lives in
+// registers as B fragments (56 per thread).  The legacy mma.sync path is the right tool for K = 108, N = 32: a tcgen05
+// tile would spend its time waiting for the gather, not in the tensor core.
+constexpr int kStemTH = 8, kStemTW = 32;                 // output tile
+constexpr int kStemPH = 2 * kStemTH + 4, kStemPW = 2 * kStemTW + 4;  // input patch 20 x 68
+constexpr int kStemPlane = kStemPH * kStemPW;           // 1360 halves per channel
+
+// same SiLU as the GEMM epilogue (gemm_sm100.cuh)
+__device__ __forceinline__ float stem_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+__device__ __forceinline__ void mma_m16n8k16_f16f32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) yolo_stem_kernel(const float* __restrict__ img, const __half* __restrict__ w /*[32,112]*/,
+                                                        const float* __restrict__ bias, __half* __restrict__ out, int ld_out,
+                                                        int B, int H, int W) {
+  __shared__ __align__(16) __half patch[3 * kStemPlane];
+  __shared__ __align__(16) __half stage[8][32 * 32];  // per warp: 32 pixels x 32 channels
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles_x = (Wo + kStemTW - 1) / kStemTW, tiles_y = (Ho + kStemTH - 1) / kStemTH;
+  const int num_tiles = B * tiles_y * tiles_x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+
+  // B fragments: for n-tile nt and k-step ks, b0 = W[n = nt*8 + g][k = ks*16 + 2t, +1], b1 = same with k + 8
+  uint32_t bf[4][7][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 7; ++ks) {
+      const __half* wr = w + (nt * 8 + g) * 112 + ks * 16 + 2 * t;
+      bf[nt][ks][0] = *reinterpret_cast<const uint32_t*>(wr);
+      bf[nt][ks][1] = *reinterpret_cast<const uint32_t*>(wr + 8);
+    }
+  // patch offset (in halves) of k = ks*16 + 2t (+8): c*plane + ky*PW + kx; padded columns (k >= 108, zero weights) -> 0
+  int koff[7][2];
+#pragma unroll
+  for (int ks = 0; ks < 7; ++ks)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int k = ks * 16 + 2 * t + 8 * h2;
+      koff[ks][h2] = (k < 108) ? (k / 36) * kStemPlane + ((k % 36) / 6) * kStemPW + (k % 6) : 0;
+    }
+  float bv[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bv[nt][0] = bias[nt * 8 + 2 * t];
+    bv[nt][1] = bias[nt * 8 + 2 * t + 1];
+  }
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int oy0 = ty * kStemTH, ox0 = tx * kStemTW;
+    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
+    __syncthreads();  // previous tile's readers are done with the patch
+    for (int i = threadIdx.x; i < 3 * kStemPlane; i += 256) {
+      const int c = i / kStemPlane, r = (i % kStemPlane) / kStemPW, x = i % kStemPW;
+      const int iy = iy0 + r, ix = ix0 + x;
+      float v = 0.f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
+      patch[i] = __float2half_rn(v);
+    }
+    __syncthreads();
+    const int oy = oy0 + warp;  // this warp's output row
+    float acc[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      // fragment rows g and g + 8 of this m-tile = output pixels ox0 + mt*16 + g (+8)
+      const __half* p0 = patch + (2 * warp) * kStemPW + 2 * (mt * 16 + g);
+      const __half* p1 = p0 + 16;  // 8 pixels further = 16 input columns
+#pragma unroll
+      for (int ks = 0; ks < 7; ++ks) {
+        uint32_t a[4];
+        a[0] = *reinterpret_cast<const uint32_t*>(p0 + koff[ks][0]);
+        a[1] = *reinterpret_cast<const uint32_t*>(p1 + koff[ks][0]);
+        a[2] = *reinterpret_cast<const uint32_t*>(p0 + koff[ks][1]);
+        a[3] = *reinterpret_cast<const uint32_t*>(p1 + koff[ks][1]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_m16n8k16_f16f32(acc[mt][nt], a, bf[nt][ks][0], bf[nt][ks][1]);
+      }
+    }
+    // bias + SiLU -> fp16, staged per warp so every global store is a 16-byte vector of one pixel's channels
+    __half* st = stage[warp];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int px = mt * 16 + g, ch = nt * 8 + 2 * t;
+        *reinterpret_cast<__half2*>(st + px * 32 + ch) =
+            __floats2half2_rn(stem_silu(acc[mt][nt][0] + bv[nt][0]), stem_silu(acc[mt][nt][1] + bv[nt][1]));
+        *reinterpret_cast<__half2*>(st + (px + 8) * 32 + ch) =
+            __floats2half2_rn(stem_silu(acc[mt][nt][2] + bv[nt][0]), stem_silu(acc[mt][nt][3] + bv[nt][1]));
+      }
+    __syncwarp();
+    if (oy < Ho) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int v = i * 32 + lane;  // vector index: pixel v / 4, 8-channel group v % 4
+        const int px = v >> 2, cg = v & 3;
+        if (ox0 + px < Wo)
+          *reinterpret_cast<uint4*>(out + ((static_cast<long long>(b) * Ho + oy) * Wo + ox0 + px) * ld_out + cg * 8) =
+              *reinterpret_cast<const uint4*>(st + px * 32 + cg * 8);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// 3x3, pad 1, stride s: NHWC fp16 (pixel pitch ld_in) -> [B*Ho*Wo, 9*C], column = (ky*3 + kx)*C + c.
+// One 16-byte vector per thread; C / 8 is a power of two and the index fits 32 bits (host checks), so the index
+// arithmetic is shifts, one constant division and two 32-bit divisions -- the first version's 64-bit runtime
+// divisions (six per vector) held the kernel at ~1.9 TB/s.
+template <int LOG_VPT>
 __global__ void __launch_bounds__(256) yolo_im2col3_kernel(const __half* __restrict__ in, int ld_in,
-                                                           __half* __restrict__ col, int B, int H, int W, int C,
-                                                           int stride) {
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const int vpt = C / 8;
-  const long long total = static_cast<long long>(B) * Ho * Wo * 9 * vpt;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % vpt);
-    const int tap = static_cast<int>((i / vpt) % 9);
-    const long long row = i / (static_cast<long long>(vpt) * 9);
-    const int ox = static_cast<int>(row % Wo);
-    const int oy = static_cast<int>((row / Wo) % Ho);
-    const int b = static_cast<int>(row / (static_cast<long long>(Wo) * Ho));
-    const int iy = oy * stride - 1 + tap / 3, ix = ox * stride - 1 + tap % 3;
+                                                           __half* __restrict__ col, int H, int W, int stride,
+                                                           unsigned Ho, unsigned Wo, unsigned total) {
+  constexpr unsigned VPT = 1u << LOG_VPT;
+  const unsigned C = VPT * 8;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cv = i & (VPT - 1);
+    const unsigned t = i >> LOG_VPT;
+    const unsigned row = t / 9u, tap = t - row * 9u;
+    const unsigned r2 = row / Wo, ox = row - r2 * Wo;
+    const unsigned b = r2 / Ho, oy = r2 - b * Ho;
+    const unsigned ky = tap / 3u, kx = tap - ky * 3u;
+    const int iy = static_cast<int>(oy) * stride - 1 + static_cast<int>(ky), ix = static_cast<int>(ox) * stride - 1 + static_cast<int>(kx);
     uint4 v = make_uint4(0, 0, 0, 0);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W)
       v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * H + iy) * W + ix) * ld_in + cv * 8);
-    *reinterpret_cast<uint4*>(col + row * (9LL * C) + tap * C + cv * 8) = v;
+    *reinterpret_cast<uint4*>(col + static_cast<long long>(row) * (9u * C) + tap * C + cv * 8) = v;
   }
 }
 
@@ -237,7 +364,7 @@ static std::vector<ConvSpec> yolo_specs() {
 
 static inline int grid_for(long long total) {
   long long g = (total + 255) / 256;
-  const long long cap = 148LL * 16;
+  const long long cap = 148LL * 32;
   return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
@@ -281,7 +408,17 @@ struct YoloRun {
     if (static_cast<size_t>(rows) * cw.kdim > h->col_elems) { status = fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small"); return; }
     {
       KernelScope ks(PROF_CONV_IM2COL, s);
-      yolo_im2col3_kernel<<<grid_for(rows * 9 * (cw.cin / 8)), 256, 0, s>>>(in.p, in.ld, h->col, B, H, W, cw.cin, cw.s);
+      const long long total = rows * 9 * (cw.cin / 8);
+      if (total >= (1LL << 32)) { status = fail(EFFOCR_ERR_INVALID, "yolo: batch too large for the 32-bit im2col index"); return; }
+      const int grid = grid_for(total);
+      const unsigned tot = static_cast<unsigned>(total);
+      switch (cw.cin) {
+        case 32: yolo_im2col3_kernel<2><<<grid, 256, 0, s>>>(in.p, in.ld, h->col, H, W, cw.s, Ho, Wo, tot); break;
+        case 64: yolo_im2col3_kernel<3><<<grid, 256, 0, s>>>(in.p, in.ld, h->col, H, W, cw.s, Ho, Wo, tot); break;
+        case 128: yolo_im2col3_kernel<4><<<grid, 256, 0, s>>>(in.p, in.ld, h->col, H, W, cw.s, Ho, Wo, tot); break;
+        case 256: yolo_im2col3_kernel<5><<<grid, 256, 0, s>>>(in.p, in.ld, h->col, H, W, cw.s, Ho, Wo, tot); break;
+        default: status = fail(EFFOCR_ERR_INVALID, "yolo: 3x3 conv input channels must be 32, 64, 128 or 256"); return;
+      }
     }
     gemm(h->col, cw.kdim, rows, cw, out, resid);
   }
@@ -329,12 +466,24 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
   // layer 0
   {
     const ConvW& cw = h->convs[r.conv_i++];
-    if (static_cast<size_t>(p1) * 112 > h->col_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small");
-    {
-      KernelScope ks(PROF_CONV_IM2COL, s);
-      yolo_im2col0_kernel<<<grid_for(p1 * 14), 256, 0, s>>>(img, h->col, B, H, W);
+    static const bool stem_gemm = [] {
+      const char* e = getenv("EFFOCR_YOLO_STEM");  // "gemm" = explicit im2col + tcgen05 GEMM (first version; A/B runs)
+      return e && e[0] == 'g';
+    }();
+    if (stem_gemm) {
+      if (static_cast<size_t>(p1) * 112 > h->col_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small");
+      {
+        KernelScope ks(PROF_CONV_IM2COL, s);
+        yolo_im2col0_kernel<<<grid_for(p1 * 14), 256, 0, s>>>(img, h->col, B, H, W);
+      }
+      r.gemm(h->col, 112, p1, cw, x0, nullptr);
+    } else {
+      const int tiles = B * ((H1 + kStemTH - 1) / kStemTH) * ((W1 + kStemTW - 1) / kStemTW);
+      const int grid = tiles < 148 * 2 ? tiles : 148 * 2;  // persistent, 2 CTAs per SM (128 registers)
+      KernelScope ks(PROF_YOLO_MISC, s);
+      yolo_stem_kernel<<<grid, 256, 0, s>>>(img, cw.w, cw.b, x0.p, x0.ld, B, H, W);
+      EFFOCR_CUDA(cudaGetLastError());
     }
-    r.gemm(h->col, 112, p1, cw, x0, nullptr);
   }
   r.conv3(x0, H1, W1, x1);                              // 1
   r.c3(x1, 64, 1, true, H2, W2, x2);                    // 2

@@ -88,7 +88,10 @@ class EffOCRPipeline:
         shape = self.localizer._input_shape
         if packed is None:
             packed = ops.pack_images(images_rgb)
-        x = ops.letterbox_resize(packed[0], packed[1], [im.shape[:2] for im in images_rgb], shape[0], shape[1])
+        buf = getattr(self, "_letterbox_buf", None)
+        if buf is None or buf.shape[0] < len(images_rgb) or tuple(buf.shape[2:]) != tuple(shape):
+            buf = self._letterbox_buf = torch.empty((len(images_rgb), 3, shape[0], shape[1]), device="cuda", dtype=torch.float32)
+        x = ops.letterbox_resize(packed[0], packed[1], [im.shape[:2] for im in images_rgb], shape[0], shape[1], out=buf)
         out, cnt = self.localizer.run_device(x)
         out, cnt = out.cpu(), cnt.cpu().tolist()
         return [out[i, :cnt[i]] for i in range(len(images_rgb))]

@@ -127,7 +127,8 @@ def letterbox_pad(pixels: torch.Tensor, images: torch.Tensor, n_images: int, hei
     return out
 
 
-def letterbox_resize(pixels: torch.Tensor, images: torch.Tensor, shapes, height: int, width: int) -> torch.Tensor:
+def letterbox_resize(pixels: torch.Tensor, images: torch.Tensor, shapes, height: int, width: int,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
     """u8 RGB line images of any size -> the reference's letterboxed model input, f32 [n, 3, height, width], on the
     device: cv2.resize(INTER_LINEAR) restated bit-exactly + grey padding + / 255 (EffLocalizer.load_localizer_img).
     shapes: [(h, w)] of the packed images (host side, for the tap tables)."""
@@ -138,7 +139,11 @@ def letterbox_resize(pixels: torch.Tensor, images: torch.Tensor, shapes, height:
     plans, taps = letterbox_plan(list(shapes), (height, width))
     d_plans = torch.from_numpy(plans.view(np.uint8).copy()).to(pixels.device, non_blocking=True)
     d_taps = torch.from_numpy(taps).to(pixels.device, non_blocking=True)
-    out = torch.empty((len(plans), 3, height, width), device=pixels.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((len(plans), 3, height, width), device=pixels.device, dtype=torch.float32)
+    else:  # caller-owned buffer (the pipeline keeps one per model shape: no allocator traffic per batch)
+        out = _cuda(out, torch.float32, "out")[:len(plans)]
+        assert out.shape[1:] == (3, height, width) and out.is_contiguous()
     _lib.check(lib.effocr_letterbox_resize(pixels.data_ptr(), images.data_ptr(), d_plans.data_ptr(), d_taps.data_ptr(),
                                            len(plans), height, width, out.data_ptr(), _lib.stream_ptr()),
                "effocr_letterbox_resize")

@@ -112,11 +112,15 @@ def glyph_images(n: int, size: int = 64):
     return [glyph_image(i, size) for i in range(n)]
 
 
-def random_yolov5s_state_dict(nc: int = 2, seed: int = 0, obj_bias: float | None = None, char_bias: float = 2.0):
+def random_yolov5s_state_dict(nc: int = 2, seed: int = 0, obj_bias: float | None = None, char_bias: float = 2.0,
+                              obj_gain: float = 1.0):
     """Random-init YOLOv5s (ultralytics `model.{i}...` keys; width 0.50 / depth 0.33) for benchmarks and smoke
     runs -- there is no network for checkpoints.  Kaiming-uniform convolutions, near-identity BatchNorm statistics,
     Detect biases a la ultralytics (`obj <- log(8 / (640 / s)^2)` unless `obj_bias` is given); `char_bias` is added to
-    the class-0 (character) logit so that, as with a trained EffOCR localizer, most surviving boxes are characters."""
+    the class-0 (character) logit so that, as with a trained EffOCR localizer, most surviving boxes are characters;
+    `obj_gain` scales the objectness rows of the Detect convolutions (a random-init head gives every location nearly
+    the same confidence; a gain of ~25 spreads the scores like a trained detector's, so box counts are not
+    hyper-sensitive to the threshold)."""
     import math
 
     import torch
@@ -164,7 +168,9 @@ def random_yolov5s_state_dict(nc: int = 2, seed: int = 0, obj_bias: float | None
     strides = (8, 16, 32)
     for l, (c, s) in enumerate(zip((128, 256, 512), strides)):
         bound = 1.0 / math.sqrt(c)
-        sd[f"model.24.m.{l}.weight"] = (torch.rand(3 * no, c, 1, 1, generator=g) * 2 - 1) * bound
+        wdet = (torch.rand(3 * no, c, 1, 1, generator=g) * 2 - 1) * bound
+        wdet.view(3, no, c)[:, 4] *= obj_gain
+        sd[f"model.24.m.{l}.weight"] = wdet
         b = ((torch.rand(3 * no, generator=g) * 2 - 1) * bound).view(3, no)
         b[:, 4] += math.log(8 / (640 / s) ** 2) if obj_bias is None else obj_bias
         b[:, 5:] += math.log(0.6 / (nc - 0.99999))
@@ -173,4 +179,30 @@ def random_yolov5s_state_dict(nc: int = 2, seed: int = 0, obj_bias: float | None
     anchors = torch.tensor((((10, 13), (16, 30), (33, 23)), ((30, 61), (62, 45), (59, 119)), ((116, 90), (156, 198), (373, 326))),
                            dtype=torch.float32)
     sd["model.24.anchors"] = anchors / torch.tensor(strides, dtype=torch.float32).view(3, 1, 1)
+    return sd
+
+
+def background_suppressed_yolo_state(nc: int = 2, seed: int = 0, obj_gain: float = 25.0, background_logit: float = -5.0,
+                                     input_shape=(640, 640)):
+    """random_yolov5s_state_dict whose objectness biases are shifted so that the uniform grey letterbox padding scores
+    `background_logit` at every scale / anchor (a random-init head otherwise gives the padding -- 94 % of a
+    letterboxed 64 x 1024 line -- one constant confidence that thousands of boxes tie on).  Needs the GPU engine:
+    the padding response is measured by one forward pass over an all-grey image."""
+    import torch
+
+    from .localizer_engine import YoloEngine
+
+    sd = random_yolov5s_state_dict(nc=nc, seed=seed, obj_bias=0.0, obj_gain=obj_gain)
+    eng = YoloEngine(sd, max_batch=1, max_shape=tuple(input_shape))
+    grey = torch.full((1, 3, input_shape[0], input_shape[1]), 114.0 / 255.0, device="cuda", dtype=torch.float32)
+    pred = eng.forward(grey)[0].float().cpu()
+    del eng
+    no, pos = 5 + nc, 0
+    for l, s in enumerate((8, 16, 32)):
+        ny, nx = input_shape[0] // s, input_shape[1] // s
+        p = pred[pos:pos + 3 * ny * nx, 4].view(3, ny, nx)
+        pos += 3 * ny * nx
+        inner = p[:, ny // 4:ny - ny // 4, nx // 4:nx - nx // 4].reshape(3, -1).median(dim=1).values.clamp(1e-6, 1 - 1e-6)
+        logit = torch.log(inner / (1 - inner))
+        sd[f"model.24.m.{l}.bias"].view(3, no)[:, 4] += background_logit - logit
     return sd

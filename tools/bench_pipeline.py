@@ -15,7 +15,7 @@ batch_lines = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 torch.manual_seed(0)
 net = TimmViTParams("vit_small_patch16_224")
 vsd = {"net." + k: v.detach().clone() for k, v in net.state_dict().items()}
-ysd = synth.random_yolov5s_state_dict(nc=2, seed=0, obj_bias=-0.5)
+ysd = synth.background_suppressed_yolo_state(nc=2, seed=0)
 g = torch.Generator().manual_seed(1)
 index = torch.nn.functional.normalize(torch.randn(10000, 384, generator=g), dim=1)
 loc = EffLocalizer(ysd, iou_thresh=0.01, conf_thresh=0.35, input_shape=(640, 640), max_batch=batch_lines)
@@ -38,8 +38,9 @@ pred = loc._eng_net.forward(x)
 lo, hi = 0.001, 0.999
 for _ in range(18):
     mid = 0.5 * (lo + hi)
-    _, cnt = nms_device(pred, mid, 0.01)
-    if float(cnt.float().mean()) > 32:
+    o_, cnt = nms_device(pred, mid, 0.01)
+    live_ = torch.arange(o_.shape[1], device=o_.device)[None, :] < cnt[:, None]
+    if float(((o_[:, :, 5] == 0) & live_).sum()) / len(chunk) > 32:
         lo = mid
     else:
         hi = mid
