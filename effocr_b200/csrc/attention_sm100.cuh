@@ -431,4 +431,581 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_cons
   if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ 16-softmax-warp variant (default)
+constexpr int kAt16Threads = 128 + 16 * 32;
+constexpr int kAt16SmemBytes = kAtSmemBytes + 2 * 2 * 2 * 128 * 4;
+__device__ __forceinline__ void named_bar_sync_at(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kAt16Threads, 1)
+attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                    __half* __restrict__ out, int batch, int H, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
+  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // [2 pair parities] x 26 KB
+  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 26 KB
+  uint8_t* smem_p = smem_v + kAtKVBytes;               // [2 groups] x 52 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;     // [2]
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_empty = bars + 9;
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* o_full = bars + 14;    // [2]
+  uint64_t* t_free = bars + 16;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* xch = reinterpret_cast<float*>(bars + 32);  // [max | sum][group][column half][128 rows]
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int D = H * 64;
+  const int num_bh = batch * H;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);   // both column halves of the group
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 8);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ---------------- TMA producer
+    if (elect_one_sync()) {
+      int it = 0;  // pair counter of this CTA
+      for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+        const int b = bh / H, h = bh % H;
+        const int row0 = b * kAtT;
+        const int s = it & 1;
+        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
+        mbar_wait(&k_empty[s], par2 ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], kAtKVBytes);
+        tma_load_2d(&tma_kv, &k_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_empty[g], par ^ 1);
+          mbar_arrive_expect_tx(&q_full[g], kAtQBytes);
+          tma_load_2d(&tma_q, &q_full[g], smem_q + g * kAtQBytes, h * 64, row0 + g * 128);
+        }
+        mbar_wait(v_empty, par ^ 1);
+        mbar_arrive_expect_tx(v_full, kAtKVBytes);
+        tma_load_2d(&tma_kv, v_full, smem_v, 2 * D + h * 64, row0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ---------------- MMA issuer.  Issue order per pair i:  S0(i), PV1(i-1), S1(i), PV0(i)  -- the two query-tile
+    // groups run half a period out of phase, so one group's MUFU-bound softmax overlaps the other group's MMAs,
+    // TMEM waits and epilogue instead of both groups competing for the MUFU pipe and then idling together.
+    // The whole warp walks the loop (waits and descriptor arithmetic stay warp-uniform, i.e. in uniform registers);
+    // only the tcgen05 instructions are predicated on one elected lane -- issuing from inside an `if (elect_one)`
+    // region costs a R2UR waterfall of ~16 instructions per MMA, three times the 32 cycles an N = 64 MMA runs for.
+    {
+      const bool leader_lane = elect_one_sync();
+      constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
+      constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
+      const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
+      auto issue_s = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        const int s = it & 1;
+        mbar_wait(&q_full[g], par);
+        mbar_wait(&t_free[g], par ^ 1);  // region g (S/O columns) drained by the previous pair's epilogue
+        tcgen05_fence_after();
+        const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
+        const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
+        if (leader_lane) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(&q_empty[g]);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        mbar_wait(&p_full[g], par);  // all four warps of the group have read S_g and written P_g
+        tcgen05_fence_after();
+        const uint32_t pbase = p_base + g * kAtPBytes;
+        if (leader_lane) {
+#pragma unroll
+          for (int ks = 0; ks < 12; ++ks) {
+            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+          }
+          umma_f16(tmem_base + g * kAtTmemRegion, make_sw32_kmajor_desc(pbase + kAtPMain),
+                   make_sw128_mnmajor_desc(v_base + 12 * 2048), idesc_o, 1u);
+          umma_commit(&o_full[g]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader_lane) umma_commit(bar);
+        __syncwarp();
+      };
+      int it = 0;
+      for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(&k_full[s], (it >> 1) & 1);
+        issue_s(0, it);
+        if (it > 0) {
+          issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
+          commit(v_empty);
+        }
+        issue_s(1, it);
+        commit(&k_empty[s]);
+        mbar_wait(v_full, it & 1);  // V(it), reloaded after PV1(it-1) retired
+        issue_pv(0, it);
+      }
+      if (it > 0) {
+        issue_pv(1, it - 1);
+        commit(v_empty);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ---------------- softmax + epilogue, SIXTEEN warps: a query row is shared by two threads (same TMEM lane, warps
+    // with equal warp_idx % 4), each owning one half of the key columns (keys 0..111 / 112..207, 16-column chunks) and
+    // one half of the output columns.  Row maximum and row sum are exchanged through shared memory under a 64-thread
+    // named barrier.  Four softmax warps per scheduler instead of two: the MUFU pipe and the TMEM loads of one warp
+    // hide behind the arithmetic of the others (the 8-warp version ran at XU 41 %, issue 29 %: latency-bound).
+    const int w = warp_idx - 4;
+    const int q = warp_idx & 3;
+    const int g = (w >> 2) & 1;
+    const int hc = w >> 3;
+    const int r = q * 32 + lane;  // row inside the 128-row tile
+    const int pair_bar = 1 + g * 4 + q;
+    const int c0 = hc ? 7 : 0, nch = hc ? 6 : 7;  // my 16-column chunks: [c0, c0 + nch)
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
+    uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
+    uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    float* my_max = xch + ((0 * 2 + g) * 2 + hc) * 128 + r;
+    float* peer_max = xch + ((0 * 2 + g) * 2 + (hc ^ 1)) * 128 + r;
+    float* my_sum = xch + ((1 * 2 + g) * 2 + hc) * 128 + r;
+    float* peer_sum = xch + ((1 * 2 + g) * 2 + (hc ^ 1)) * 128 + r;
+    int it = 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+      const int b = bh / H, h = bh % H;
+      const uint32_t par = it & 1;
+      mbar_wait(&s_full[g], par);
+      tcgen05_fence_after();
+      // pass 1: maximum over my valid keys (chunk i+1 in flight while chunk i is reduced)
+      float mx;
+      {
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        uint32_t v[2][16];
+        tmem_ld_32x32b_x16(trow + c0 * 16, v[0]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          if (i < nch) {
+            tmem_ld_wait();
+            if (i + 1 < nch) tmem_ld_32x32b_x16(trow + (c0 + i + 1) * 16, v[(i + 1) & 1]);
+            const int nvalid = (c0 + i == 12) ? 5 : 16;  // keys 192..196 are the last valid ones
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (e < nvalid) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[i & 1][e]));
+          }
+        }
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      }
+      *my_max = mx;
+      named_bar_sync_at(pair_bar, 64);
+      mx = fmaxf(mx, *peer_max);
+      const float moff = mx * scale_log2e;
+      // pass 2: p = 2^(s * scale - max * scale), partial row sum, P -> smem (fp16, K-major, swizzled)
+      float sum;
+      {
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t v[2][16];
+        tmem_ld_32x32b_x16(trow + c0 * 16, v[0]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          if (i < nch) {
+            const int c = c0 + i;
+            tmem_ld_wait();
+            if (i + 1 < nch) tmem_ld_32x32b_x16(trow + (c + 1) * 16, v[(i + 1) & 1]);
+            float p[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              p[e] = (c == 12 && e >= 5) ? 0.f : ex2_approx(fmaf(__uint_as_float(v[i & 1][e]), scale_log2e, -moff));
+              s4[e & 3] += p[e];
+            }
+            uint4 pk[2];
+            __half2* ph = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) ph[t] = __floats2half2_rn(p[2 * t], p[2 * t + 1]);
+            if (c < 12) {
+              uint8_t* chunk = pmain + (c >> 2) * kAtQBytes;
+              const int piece = (c & 3) * 2;  // 16-byte pieces inside the 64-key SWIZZLE_128B chunk
+              *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
+              *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+            } else {
+              *reinterpret_cast<uint4*>(ptail + ((0 ^ ((r >> 2) & 1)) << 4)) = pk[0];  // SWIZZLE_32B: bit 4 ^= bit 7
+              *reinterpret_cast<uint4*>(ptail + ((1 ^ ((r >> 2) & 1)) << 4)) = pk[1];
+            }
+          }
+        }
+        sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      *my_sum = sum;
+      tcgen05_fence_before();
+      // P written: make the generic-proxy writes visible to the MMA (async proxy), then signal
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      // epilogue: O / sum -> fp16 -> global; this thread owns output columns hc*32 .. +32
+      mbar_wait(&o_full[g], par);
+      tcgen05_fence_after();
+      named_bar_sync_at(pair_bar, 64);  // partner's partial sum is visible; its reads of my max are done
+      const float inv = 1.0f / (sum + *peer_sum);
+      const int tok = g * 128 + r;
+      __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64 + hc * 32;
+      uint32_t o[2][16];
+      tmem_ld_32x32b_x16(trow + hc * 32, o[0]);
+      tmem_ld_32x32b_x16(trow + hc * 32 + 16, o[1]);
+      tmem_ld_wait();
+      tcgen05_fence_before();  // my part of O is read: region g is free for the next pair's S once all 8 warps arrive
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_free[g]);
+      if (tok < kAtT) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 pk;
+          __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            ph[t] = __floats2half2_rn(__uint_as_float(o[j >> 1][(8 * j + 2 * t) & 15]) * inv,
+                                      __uint_as_float(o[j >> 1][(8 * j + 2 * t + 1) & 15]) * inv);
+          *reinterpret_cast<uint4*>(dst + 8 * j) = pk;
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ one TMEM pass, two key blocks (default)
+__global__ void __launch_bounds__(kAtThreads, 1)
+attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                    __half* __restrict__ out, int batch, int H, float scale_log2e) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
+  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // [2 pair parities] x 26 KB
+  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 26 KB
+  uint8_t* smem_p = smem_v + kAtKVBytes;               // [2 groups] x 52 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;     // [2]
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_empty = bars + 9;
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]
+  uint64_t* o_full = bars + 14;    // [2]
+  uint64_t* t_free = bars + 16;    // [2]
+  uint64_t* pb_full = bars + 18;   // [2] second key block of P written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int D = H * 64;
+  const int num_bh = batch * H;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pb_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 4);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ---------------- TMA producer
+    if (elect_one_sync()) {
+      int it = 0;  // pair counter of this CTA
+      for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+        const int b = bh / H, h = bh % H;
+        const int row0 = b * kAtT;
+        const int s = it & 1;
+        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
+        mbar_wait(&k_empty[s], par2 ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], kAtKVBytes);
+        tma_load_2d(&tma_kv, &k_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_empty[g], par ^ 1);
+          mbar_arrive_expect_tx(&q_full[g], kAtQBytes);
+          tma_load_2d(&tma_q, &q_full[g], smem_q + g * kAtQBytes, h * 64, row0 + g * 128);
+        }
+        mbar_wait(v_empty, par ^ 1);
+        mbar_arrive_expect_tx(v_full, kAtKVBytes);
+        tma_load_2d(&tma_kv, v_full, smem_v, 2 * D + h * 64, row0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ---------------- MMA issuer (warp-uniform loop, tcgen05 issue predicated on one elected lane).
+    // Issue order per pair i:  S0(i), PV1a(i-1), PV1b(i-1), S1(i), PV0a(i), PV0b(i).
+    {
+      const bool leader_lane = elect_one_sync();
+      constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
+      constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
+      const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
+      auto issue_s = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        const int s = it & 1;
+        mbar_wait(&q_full[g], par);
+        mbar_wait(&t_free[g], par ^ 1);  // region g (S / O1 / O2 columns) drained by the previous pair's epilogue
+        tcgen05_fence_after();
+        const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
+        const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
+        if (leader_lane) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+          umma_commit(&q_empty[g]);
+          umma_commit(&s_full[g]);
+        }
+        __syncwarp();
+      };
+      // O1 (TMEM columns 0..63 of the region) = P[:, 0:128] V[0:128];  O2 (columns 64..127) = P[:, 128:208] V[128:208]
+      auto issue_pv = [&](int g, int it) {
+        const uint32_t par = it & 1;
+        const uint32_t pbase = p_base + g * kAtPBytes;
+        mbar_wait(&p_full[g], par);  // key block A of P written, S columns 0..127 consumed by all four warps
+        tcgen05_fence_after();
+        if (leader_lane) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+        mbar_wait(&pb_full[g], par);  // key block B written, all of S consumed
+        tcgen05_fence_after();
+        if (leader_lane) {
+#pragma unroll
+          for (int ks = 8; ks < 12; ++ks) {
+            const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
+            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            umma_f16(tmem_base + g * kAtTmemRegion + 64, dp, dv, idesc_o, ks > 8 ? 1u : 0u);
+          }
+          umma_f16(tmem_base + g * kAtTmemRegion + 64, make_sw32_kmajor_desc(pbase + kAtPMain),
+                   make_sw128_mnmajor_desc(v_base + 12 * 2048), idesc_o, 1u);
+          umma_commit(&o_full[g]);
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (leader_lane) umma_commit(bar);
+        __syncwarp();
+      };
+      int it = 0;
+      for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+        const int s = it & 1;
+        mbar_wait(&k_full[s], (it >> 1) & 1);
+        issue_s(0, it);
+        if (it > 0) {
+          issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
+          commit(v_empty);
+        }
+        issue_s(1, it);
+        commit(&k_empty[s]);
+        mbar_wait(v_full, it & 1);  // V(it), reloaded after PV1(it-1) retired
+        issue_pv(0, it);
+      }
+      if (it > 0) {
+        issue_pv(1, it - 1);
+        commit(v_empty);
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ---------------- softmax + epilogue: group g = query tile, thread = query row.  ONE pass over S in TMEM
+    // (tcgen05.ld moves ~64 B/clk/SM and reading S twice bounded the two-pass kernel): the keys are split into block A
+    // (0..127) and block B (128..196); a block is pulled into registers once, reduced to its own maximum, exponentiated
+    // against THAT maximum and written to the P tile; P_A V_A and P_B V_B accumulate into separate TMEM tiles
+    // (flash-attention style) and the epilogue combines them with the factors 2^(m_A - m), 2^(m_B - m).
+    const int g = (warp_idx - 4) >> 2;
+    const int q = warp_idx & 3;
+    const int r = q * 32 + lane;  // row inside the 128-row tile
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
+    uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
+    uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    int it = 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+      const int b = bh / H, h = bh % H;
+      const uint32_t par = it & 1;
+      mbar_wait(&s_full[g], par);
+      tcgen05_fence_after();
+      float mA = 0.f, mB = 0.f, lA = 1.f, lB = 1.f;
+      // rows 224..255 (group 1, lane quarter 3) do not exist (197 tokens): that warp only keeps the hand-shakes going;
+      // whatever its P rows hold feeds only output rows that are never stored
+      const bool live = !(g == 1 && q == 3);
+      if (live) {  // ---- block A: keys 0..127
+        uint32_t v[8][16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tmem_ld_32x32b_x16(trow + c * 16, v[c]);
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+          for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
+        mA = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float moff = mA * scale_log2e;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint4 pk[2];
+          __half2* ph = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff));
+            s4[(2 * t) & 3] += p0;
+            s4[(2 * t + 1) & 3] += p1;
+            ph[t] = __floats2half2_rn(p0, p1);
+          }
+          uint8_t* chunk = pmain + (c >> 2) * kAtQBytes;
+          const int piece = (c & 3) * 2;
+          *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
+          *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+        }
+        lA = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (live) {  // ---- block B: keys 128..207 (valid up to 196)
+        uint32_t v[5][16];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) tmem_ld_32x32b_x16(trow + 128 + c * 16, v[c]);
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c = 0; c < 5; ++c)
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c < 4 || e < 5) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
+        mB = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        const float moff = mB * scale_log2e;
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          uint4 pk[2];
+          __half2* ph = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const bool ok0 = c < 4 || 2 * t < 5, ok1 = c < 4 || 2 * t + 1 < 5;  // keys >= 197 masked
+            const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff)) : 0.f;
+            const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff)) : 0.f;
+            s4[(2 * t) & 3] += p0;
+            s4[(2 * t + 1) & 3] += p1;
+            ph[t] = __floats2half2_rn(p0, p1);
+          }
+          if (c < 4) {
+            uint8_t* chunk = pmain + 2 * kAtQBytes;
+            const int piece = c * 2;
+            *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
+            *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+          } else {
+            *reinterpret_cast<uint4*>(ptail + ((0 ^ ((r >> 2) & 1)) << 4)) = pk[0];  // SWIZZLE_32B: bit 4 ^= bit 7
+            *reinterpret_cast<uint4*>(ptail + ((1 ^ ((r >> 2) & 1)) << 4)) = pk[1];
+          }
+        }
+        lB = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pb_full[g]);
+      // ---- epilogue: (O1 * aA + O2 * aB) / (lA * aA + lB * aB) -> fp16 -> global
+      const float m = fmaxf(mA, mB);
+      const float aA = ex2_approx((mA - m) * scale_log2e), aB = ex2_approx((mB - m) * scale_log2e);
+      const float inv = 1.0f / fmaf(lA, aA, lB * aB);
+      const float wA = aA * inv, wB = aB * inv;
+      mbar_wait(&o_full[g], par);
+      tcgen05_fence_after();
+      const int tok = g * 128 + r;
+      __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o1[32], o2[32];
+        tmem_ld_32x32b_x32(trow + hh * 32, o1);
+        tmem_ld_32x32b_x32(trow + 64 + hh * 32, o2);
+        tmem_ld_wait();
+        if (hh == 1) {  // O fully read: region g is free for the next pair's S
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_free[g]);
+        }
+        if (tok < kAtT) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int e = 8 * j + 2 * t;
+              ph[t] = __floats2half2_rn(fmaf(__uint_as_float(o1[e]), wA, __uint_as_float(o2[e]) * wB),
+                                        fmaf(__uint_as_float(o1[e + 1]), wA, __uint_as_float(o2[e + 1]) * wB));
+            }
+            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * j) = pk;
+          }
+        }
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace effocr

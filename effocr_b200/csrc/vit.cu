@@ -86,10 +86,9 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
   return layernorm_launch<float>(x, ldx, g, b, out, ldo, rows, D, eps, s, tag);
 }
 
-// impl 0: tcgen05 kernel (attention_sm100.cuh), softmax variant chosen by kAttentionDefaultSinglePass;
-// impl 1: first-generation mma.sync kernel (kept as an A/B reference); impl 2 / 3: tcgen05 kernel with the
-// two-pass / single-pass softmax forced (A/B)
-constexpr bool kAttentionDefaultSinglePass = false;
+// impl 0: tcgen05 kernel, one TMEM pass over S with two key blocks combined flash-attention style (default); A/B
+// variants via EFFOCR_ATTENTION_SOFTMAX or impl: 2 = two TMEM passes, 3 (env 1) = single pass via fp16 deltas in the P
+// tile, 4 = two passes with 16 softmax warps; impl 1: first-generation mma.sync kernel
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
@@ -106,13 +105,19 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     if (!attr) {
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt16SmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       attr = true;
     }
     static const int env_variant = [] {
-      const char* e = getenv("EFFOCR_ATTENTION_SOFTMAX");  // "1" = single TMEM pass, "2" = two passes; for A/B runs
+      const char* e = getenv("EFFOCR_ATTENTION_SOFTMAX");
       return e ? atoi(e) : 0;
     }();
-    const bool single = impl == 3 || (impl == 0 && (env_variant == 1 || (env_variant == 0 && kAttentionDefaultSinglePass)));
+    int variant = 0;  // 0: one TMEM pass / two key blocks, 1: single pass via fp16 deltas, 2: two passes, 4: 16 warps two passes
+    if (impl == 2) variant = 2;
+    else if (impl == 3) variant = 1;
+    else if (impl == 4) variant = 4;
+    else if (env_variant == 1 || env_variant == 2 || env_variant == 4) variant = env_variant;
     const long long rows = static_cast<long long>(batch) * T;
     const int D = H * 64;
     CUtensorMap tq, tkv;
@@ -121,8 +126,10 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     const int pairs = batch * H;
     const int grid = pairs < sm_count() ? pairs : sm_count();
     KernelScope ks(PROF_ATTENTION, s);
-    if (single) attention_tc_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
-    else attention_tc_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    if (variant == 1) attention_tc_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    else if (variant == 2) attention_tc_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    else if (variant == 4) attention_tc16_kernel<<<grid, kAt16Threads, kAt16SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    else attention_tc2b_kernel<<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
