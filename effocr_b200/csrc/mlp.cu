@@ -17,7 +17,7 @@ static int launch_mlp(const MlpArgs& a, cudaStream_t stream) {
   EFFOCR_TRY(make_tmap_f16_2d(&ta, a.h, a.M, D, a.ldh, 128));
   EFFOCR_TRY(make_tmap_f16_2d(&tw1, a.w1, a.HID, D, D, 32));
   EFFOCR_TRY(make_tmap_f16_2d(&tw2, a.w2, D, a.HID, a.HID, 96));
-  EFFOCR_TRY(make_tmap_2d(&tx, a.x, 4, a.M, D, a.ldx, 32, 16, 64));
+  EFFOCR_TRY(make_tmap_2d(&tx, a.x, 4, a.M, D, a.ldx, 32, 32, 128));
   auto kern = mlp_fused_pair_kernel<D, AHEAD>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -29,7 +29,7 @@ static int launch_mlp(const MlpArgs& a, cudaStream_t stream) {
   if (tiles < pairs) pairs = tiles;
   {
     KernelScope ks(PROF_MLP_FUSED, stream);
-    kern<<<2 * pairs, kMlpThreads, Cfg::kSmemBytes, stream>>>(ta, tw1, tw2, tx, a.M, a.HID, a.b1, a.b2);
+    kern<<<2 * pairs, kMlpThreads, Cfg::kSmemBytes, stream>>>(ta, tw1, tw2, tx, a.M, a.HID, a.b1, a.b2, a.dbg);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
@@ -61,5 +61,9 @@ extern "C" int effocr_mlp_fused_f16(const void* d_h, long long ldh, const void* 
   a.w1 = reinterpret_cast<const __half*>(d_w1); a.b1 = d_b1;
   a.w2 = reinterpret_cast<const __half*>(d_w2); a.b2 = d_b2;
   a.x = d_x; a.ldx = ldx; a.M = M; a.D = D; a.HID = HID;
+  {
+    const char* e = getenv("EFFOCR_MLP_DBG_PTR");  // tools/mlp_timeline.py: device buffer of 512 int64 for the hand-off timeline
+    if (e) a.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+  }
   return effocr::mlp_fused_f16(a, reinterpret_cast<cudaStream_t>(stream));
 }

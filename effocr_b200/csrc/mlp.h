@@ -14,6 +14,7 @@ struct MlpArgs {
   float* x = nullptr;          // [M, D] fp32 residual stream, updated in place
   long long ldx = 0;
   int M = 0, D = 0, HID = 0;
+  long long* dbg = nullptr;  // optional: 512 x int64 device buffer receiving clock64() stamps (profiling aid)
 };
 
 bool mlp_fused_supported(int D, int HID);

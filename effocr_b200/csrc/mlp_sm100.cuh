@@ -92,8 +92,10 @@ template <int D, int AHEAD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w1,
                       const __grid_constant__ CUtensorMap tma_w2, const __grid_constant__ CUtensorMap tma_x, int M,
-                      int HID, const float* __restrict__ b1, const float* __restrict__ b2) {
+                      int HID, const float* __restrict__ b1, const float* __restrict__ b2, long long* __restrict__ dbg) {
   using Cfg = MlpCfg<D>;
+  // dbg != nullptr: CTA 0 logs clock64() at the pipeline hand-offs of its third tile (tools/mlp_timeline.py)
+#define MLP_DBG(slot) do { if (dbg && blockIdx.x == 0 && local == 2) dbg[(slot)] = clock64(); } while (0)
   constexpr int STAGES = Cfg::kStages;
   constexpr int KB = Cfg::kKB;
   extern __shared__ uint8_t smem_raw[];
@@ -138,7 +140,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       mbar_init(&pempty[i], 1);
     }
     mbar_init(ofull, 1);
-    mbar_init(oempty, 2 * kMlpEpiWarps);
+    mbar_init(oempty, kMlpEpiWarps);  // the eight draining warps of each CTA
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -211,6 +213,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
               for (int kb = 0; kb < KB; ++kb) mbar_wait(&afull[kb], local & 1);
             }
             tcgen05_fence_after();
+            if (leader_lane) MLP_DBG(0 * 64 + j);
             const uint32_t tmem_s = tmem_base + Cfg::kSCol + b * 64;
             const uint64_t da0 = make_sw128_kmajor_desc(a_base);
             const uint64_t db0 = make_sw128_kmajor_desc(w_base + stage * Cfg::kStageBytes);
@@ -237,6 +240,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
             mbar_wait(&pfull[b], u & 1);
             mbar_wait(&wfull[stage], phase);
             tcgen05_fence_after();
+            if (leader_lane) MLP_DBG(1 * 64 + c);
             const uint64_t dp0 = make_sw128_kmajor_desc(p_base + b * Cfg::kPBytes);
             const uint64_t dw0 = make_sw128_kmajor_desc(w_base + stage * Cfg::kStageBytes);
             if (leader_lane) {
@@ -262,7 +266,6 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
     const int cq = (warp_idx - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* stg = smem_p + (warp_idx - 4) * 2048;  // O staging: the P buffers are idle while O drains
     uint32_t local = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
       for (int j = 0; j < NCH; ++j) {
@@ -277,6 +280,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         }
         mbar_wait(&sfull[b], u & 1);
         tcgen05_fence_after();
+        if (warp_idx == 4 && lane == 0) MLP_DBG(2 * 64 + j);
         uint32_t v[16];
         tmem_ld_32x32b_x16(tmem_lane + Cfg::kSCol + b * 64 + cq * 16, v);
         tmem_ld_wait();
@@ -288,7 +292,9 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           ph[i] = gelu_erf2(pack2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bv[i]);
+        if (warp_idx == 4 && lane == 0) MLP_DBG(3 * 64 + j);
         mbar_wait(&pempty[b], (u & 1) ^ 1);  // O += P . W2^T of two chunks ago has read this buffer
+        if (warp_idx == 4 && lane == 0) MLP_DBG(4 * 64 + j);
         uint8_t* prow = smem_p + b * Cfg::kPBytes + row * 128;
         // K-major SWIZZLE_128B tile: 16-byte piece c of row r lives at piece c ^ (r & 7)
         *reinterpret_cast<uint4*>(prow + (((2 * cq) ^ (row & 7)) << 4)) = pk[0];
@@ -296,48 +302,59 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&pfull[b]);
+        if (warp_idx == 4 && lane == 0) MLP_DBG(5 * 64 + j);
       }
-      // ---- output: O + b2 -> TMA reduce-add into x
-      constexpr int OCH = D / 4 / 16;  // 16-column chunks per warp
+      // ---- output: O + b2 -> TMA reduce-add into x.  Eight warps (column halves 0 / 1 of each lane quarter) drain
+      // 32 x 32 fp32 boxes (128-byte rows, 4 KB) through the idle P buffers; the other eight only join the barrier.
+      // The kernel's own clock64 timeline (tools/mlp_timeline.py) puts this drain at ~11 000 cycles per tile -- 18 B/clk
+      // per SM, the L2 reduction rate with all CTAs draining together -- against ~1 800 cycles per hidden chunk in
+      // steady state (MMA-bound).  Tried and rejected: 16 warps x 2 KB boxes (12 300 cycles), prefetching the residual
+      // rows into L2 (no change: not an HBM-latency effect), residual add in registers with per-thread 64-byte row
+      // slices (43 000 cycles: 32 cache lines per load / store instruction).
+      constexpr int OCH = D / 2 / 32;  // 32-column chunks per draining warp
       const int m_row0 = tile * 256 + static_cast<int>(rank) * 128 + q * 32;
-      mbar_wait(ofull, local & 1);
-      tcgen05_fence_after();
-      uint32_t v[2][16];
-      tmem_ld_32x32b_x16(tmem_lane + cq * (D / 4), v[0]);
+      if (warp_idx == 4 && lane == 0) MLP_DBG(6 * 64 + 0);
+      if (cq < 2) {
+        uint8_t* stg = smem_p + ((warp_idx - 4) & 7) * 4096;
+        mbar_wait(ofull, local & 1);
+        tcgen05_fence_after();
+        if (warp_idx == 4 && lane == 0) MLP_DBG(6 * 64 + 1);
+        uint32_t v[32];
 #pragma unroll
-      for (int c = 0; c < OCH; ++c) {
-        const int col0 = cq * (D / 4) + c * 16;
-        float bv[16];
+        for (int c = 0; c < OCH; ++c) {
+          const int col0 = cq * (D / 2) + c * 32;
+          tmem_ld_32x32b_x32(tmem_lane + col0, v);
+          float bv[32];
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) {
-          const float4 t = __ldg(reinterpret_cast<const float4*>(b2 + col0 + i));
-          bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
-        }
-        tmem_ld_wait();
-        if (c + 1 < OCH) {
-          tmem_ld_32x32b_x16(tmem_lane + col0 + 16, v[(c + 1) & 1]);
-        } else {
-          tcgen05_fence_before();
+          for (int i = 0; i < 32; i += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(b2 + col0 + i));
+            bv[i] = t.x; bv[i + 1] = t.y; bv[i + 2] = t.z; bv[i + 3] = t.w;
+          }
+          tmem_ld_wait();
+          if (c + 1 == OCH) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(oempty);  // O accumulator back to the MMA issuer
+          }
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          if (lane == 0) mbar_arrive_leader(oempty);  // O accumulator back to the MMA issuer
+          // 128-byte rows, SWIZZLE_128B: 16-byte piece j of row r lives at piece j ^ (r & 7)
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((jj ^ (lane & 7)) << 4)) =
+                make_float4(__uint_as_float(v[4 * jj]) + bv[4 * jj], __uint_as_float(v[4 * jj + 1]) + bv[4 * jj + 1],
+                            __uint_as_float(v[4 * jj + 2]) + bv[4 * jj + 2], __uint_as_float(v[4 * jj + 3]) + bv[4 * jj + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_reduce_add_2d(&tma_x, stg, col0, m_row0);
+            tma_store_commit();
+          }
         }
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
-        // 64-byte rows, SWIZZLE_64B: 16-byte piece j of row r lives at piece j ^ ((r >> 1) & 3)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-          *reinterpret_cast<float4*>(stg + lane * 64 + ((jj ^ ((lane >> 1) & 3)) << 4)) =
-              make_float4(__uint_as_float(v[c & 1][4 * jj]) + bv[4 * jj], __uint_as_float(v[c & 1][4 * jj + 1]) + bv[4 * jj + 1],
-                          __uint_as_float(v[c & 1][4 * jj + 2]) + bv[4 * jj + 2], __uint_as_float(v[c & 1][4 * jj + 3]) + bv[4 * jj + 3]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_reduce_add_2d(&tma_x, stg, col0, m_row0);
-          tma_store_commit();
-        }
       }
-      if (lane == 0) tma_store_wait_read<0>();
-      __syncwarp();
+      if (warp_idx == 4 && lane == 0) MLP_DBG(6 * 64 + 2);
       named_bar_sync(1, kMlpEpiWarps * 32);  // every warp's staging reads are done before P is written again
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -345,6 +362,7 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
   tcgen05_fence_before();
   cluster_sync_all();
   if (warp_idx == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+#undef MLP_DBG
 }
 
 }  // namespace effocr
