@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline-lines", type=int, default=256,
+    ap.add_argument("--pipeline-lines", type=int, default=512,
                     help="lines per GPU for the auxiliary whole-pipeline (config C3) measurement; 0 = skip")
     ap.add_argument("--index-random", action="store_true",
                     help="profiling runs: random unit-norm prototypes instead of embedding rendered glyphs")
@@ -246,12 +246,12 @@ def time_pipeline_c3(args, rec_pipe, rank, barrier):
     loc._conf_thresh = hi
     chars = [chr(33 + i % 94) for i in range(rec_pipe.index.ntotal)]
     full = EffOCRPipeline(loc, rec_pipe, chars, lang="en", knn=1)
-    run_effocr(lines[:bl], full, batch_lines=bl)  # warm-up
+    run_effocr(lines[:2 * bl], full, batch_lines=bl)  # warm-up, through the overlapped two-batch path
     barrier()
     t0 = time.perf_counter()
     res = []
-    for i0 in range(0, L, bl):
-        res += full.infer_lines(lines[i0:i0 + bl])
+    for batch_res in full.infer_batches(lines[i0:i0 + bl] for i0 in range(0, L, bl)):  # two-stage overlapped pipeline
+        res += batch_res
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     ncrops = sum(len(r["char_boxes"]) for r in res)

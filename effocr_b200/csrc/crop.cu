@@ -53,7 +53,8 @@ __device__ __forceinline__ void numpy_slice(int start, int stop, int n, int* lo,
 }
 
 constexpr int kCropMaxStage = 3072;  // staged source pixels (float4 each) per block: 48 KB
-constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4;
+constexpr int kCropHRows = 8;        // separable path: horizontally resampled band rows kept in shared memory (28 KB)
+constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4 + kCropHRows * 224 * 16;
 
 template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16), 3 4x4-patch-major f16 ([n*3136, 48])
 __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restrict__ pixels,
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
   float4* s_src = reinterpret_cast<float4*>(crop_smem);                         // [kCropMaxStage]
   float4* s_xw = s_src + kCropMaxStage;                                         // [224] horizontal weights (<= 4 taps)
   int* s_xmn = reinterpret_cast<int*>(s_xw + OUT);                              // [224] first horizontal tap
+  float4* s_h = reinterpret_cast<float4*>(s_xmn + OUT);                         // [kCropHRows][224] horizontal pass
   bool fast = false;
   if (!empty) {
     const int S = h > w ? h : w;
@@ -123,6 +125,45 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
 #pragma unroll
       for (int yy = 0; yy < 4; ++yy) wys[yy] = yy < ty.sz ? tap_weight(ty, yy, invscale) : 0.f;
       const int oct = j0 >> 3;
+      if (nrows <= kCropHRows) {
+        // separable resampling, the order ATen itself uses (horizontal pass, then vertical): every band row is
+        // resampled to the 224 output columns once (4 taps) and each output pixel then reads <= 4 of those values,
+        // instead of 16 source pixels -- the same FMA sequence per pixel as the nested loop below (zero-weight taps
+        // add exactly 0), so the two paths are bit-identical; shared-memory traffic drops ~2.3x (the kernel ran at
+        // 97 % L1/shared pipe utilisation).
+        {
+          const int j = threadIdx.x;  // one output column per thread (blockDim.x == 224)
+          const int slot = (j & 7) * 28 + (j >> 3);
+          const int xmn = s_xmn[slot];
+          const float4 xw = s_xw[slot];
+          const float wxs[4] = {xw.x, xw.y, xw.z, xw.w};
+          for (int rr = 0; rr < nrows; ++rr) {
+            const float4* rowp = s_src + rr * S;
+            float hr = 0.f, hg = 0.f, hb = 0.f;
+#pragma unroll
+            for (int xx = 0; xx < 4; ++xx) {
+              const int x = xmn + xx < S ? xmn + xx : S - 1;
+              const float4 px = rowp[x];
+              hr = fmaf(wxs[xx], px.x, hr); hg = fmaf(wxs[xx], px.y, hg); hb = fmaf(wxs[xx], px.z, hb);
+            }
+            s_h[rr * OUT + slot] = make_float4(hr, hg, hb, 0.f);
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float r = 0.f, g = 0.f, b = 0.f;
+#pragma unroll
+          for (int yy = 0; yy < 4; ++yy) {
+            if (yy >= ty.sz) break;
+            const float4 hv = s_h[(ty.mn - r0 + yy) * OUT + k * 28 + oct];
+            r = fmaf(wys[yy], hv.x, r); g = fmaf(wys[yy], hv.y, g); b = fmaf(wys[yy], hv.z, b);
+          }
+          acc[0][k] = (r - 0.485f) / 0.229f;
+          acc[1][k] = (g - 0.456f) / 0.224f;
+          acc[2][k] = (b - 0.406f) / 0.225f;
+        }
+      } else
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int xmn = s_xmn[k * 28 + oct];

@@ -58,12 +58,13 @@ struct KnnListState {
   float minv;
   int minpos;
 };
+template <int CAP>
 __device__ __noinline__ KnnListState knn_insert(KnnListState st, float sc, int n, float* lv, int* li) {
-  if (st.count < kKnnCap) {
+  if (st.count < CAP) {
     lv[st.count * 256] = sc;
     li[st.count * 256] = n;
     ++st.count;
-    if (st.count < kKnnCap) return st;
+    if (st.count < CAP) return st;
   } else {
     lv[st.minpos * 256] = sc;
     li[st.minpos * 256] = n;
@@ -72,7 +73,7 @@ __device__ __noinline__ KnnListState knn_insert(KnnListState st, float sc, int n
   st.minpos = 0;
   int mid = -1;
 #pragma unroll 4
-  for (int s2 = 0; s2 < kKnnCap; ++s2) {
+  for (int s2 = 0; s2 < CAP; ++s2) {
     const float vv = lv[s2 * 256];
     const int ii = li[s2 * 256];
     if (vv < st.minv || (vv == st.minv && ii > mid)) { st.minv = vv; st.minpos = s2; mid = ii; }
@@ -80,6 +81,10 @@ __device__ __noinline__ KnnListState knn_insert(KnnListState st, float sc, int n
   return st;
 }
 
+// CAP: short-list length per (query, CTA half).  The union of the per-partition lists must contain the exact top-k:
+// CAP = 16 for k <= 10 (six spare places absorb re-orderings by the ~2^-22 relative error of the split-fp16 scores),
+// CAP = 32 otherwise.  Insertions cost O(CAP) and their number grows with CAP, so the short list is the epilogue's cost.
+template <int CAP>
 __global__ void __launch_bounds__(kKnnThreads, 1)
 knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_x, int B,
                      int N, int Dp, int n_tiles, int splits, float* __restrict__ part_val,
@@ -190,7 +195,7 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float sc = fmaf(__uint_as_float(v2[i]), 4.8828125e-4f, __uint_as_float(v1[i]));
-          if (n0 + i < N && (st.count < kKnnCap || sc > st.minv)) st = knn_insert(st, sc, n0 + i, lv, li);
+          if (n0 + i < N && (st.count < CAP || sc > st.minv)) st = knn_insert<CAP>(st, sc, n0 + i, lv, li);
         }
       }
       tcgen05_fence_before();
@@ -200,8 +205,8 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
     // flush this thread's short-list: partial slot = sp * 2 + half
     const int row = m0 + q * 32 + lane;
     if (row < B) {
-      const long long o = (static_cast<long long>(row) * (splits * 2) + sp * 2 + half) * kKnnCap;
-      for (int s2 = 0; s2 < kKnnCap; ++s2) {
+      const long long o = (static_cast<long long>(row) * (splits * 2) + sp * 2 + half) * CAP;
+      for (int s2 = 0; s2 < CAP; ++s2) {
         part_val[o + s2] = s2 < st.count ? lv[s2 * 256] : -INFINITY;
         part_idx[o + s2] = s2 < st.count ? li[s2 * 256] : -1;
       }
@@ -215,14 +220,14 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
 // One warp per query: merge `nparts` short-lists down to the best 32 by (approx score desc, id asc),
 // re-score those with fp32 FMAs against the fp32 index, order by (exact score desc, id asc), emit k.
 __global__ void __launch_bounds__(128) knn_merge_rerank_kernel(const float* __restrict__ part_val,
-                                                               const int* __restrict__ part_idx, int nparts,
+                                                               const int* __restrict__ part_idx, int nparts, int cap,
                                                                const float* __restrict__ q, const float* __restrict__ xb,
                                                                int B, int D, int k, float* __restrict__ out_val,
                                                                long long* __restrict__ out_idx) {
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (row >= B) return;
-  const int total = nparts * kKnnCap;
+  const int total = nparts * cap;
   const float* pv = part_val + static_cast<long long>(row) * total;
   const int* pi = part_idx + static_cast<long long>(row) * total;
   // iterative selection: 32 rounds of warp arg-max with "already taken" tracked by last (value, id)
@@ -389,18 +394,24 @@ extern "C" int effocr_knn_search(effocr_knn_t handle, const float* d_queries, in
   EFFOCR_TRY(make_tmap_f16_2d(&tx, h->xsplit, h->Npad, 3 * h->Dp, 3 * h->Dp, kKnnBN));
   static bool attr = false;
   if (!attr) {
-    EFFOCR_CUDA(cudaFuncSetAttribute(knn_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes));
+    EFFOCR_CUDA(cudaFuncSetAttribute(knn_gemm_topk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes));
+    EFFOCR_CUDA(cudaFuncSetAttribute(knn_gemm_topk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kKnnSmemBytes));
     attr = true;
   }
+  const int cap = k <= 10 ? 16 : kKnnCap;
   {
     KernelScope ks(PROF_KNN_GEMM, s);
-    knn_gemm_topk_kernel<<<m_tiles * splits, kKnnThreads, kKnnSmemBytes, s>>>(tq, tx, nq, h->N, h->Dp, n_tiles, splits,
-                                                                            h->part_val, h->part_idx);
+    if (cap == 16)
+      knn_gemm_topk_kernel<16><<<m_tiles * splits, kKnnThreads, kKnnSmemBytes, s>>>(tq, tx, nq, h->N, h->Dp, n_tiles, splits,
+                                                                                  h->part_val, h->part_idx);
+    else
+      knn_gemm_topk_kernel<32><<<m_tiles * splits, kKnnThreads, kKnnSmemBytes, s>>>(tq, tx, nq, h->N, h->Dp, n_tiles, splits,
+                                                                                  h->part_val, h->part_idx);
   }
   EFFOCR_CUDA(cudaGetLastError());
   {
     KernelScope ks(PROF_KNN_MERGE, s);
-    knn_merge_rerank_kernel<<<(nq + 3) / 4, 128, 0, s>>>(h->part_val, h->part_idx, splits * 2, d_queries, h->xb, nq,
+    knn_merge_rerank_kernel<<<(nq + 3) / 4, 128, 0, s>>>(h->part_val, h->part_idx, splits * 2, cap, d_queries, h->xb, nq,
                                                          h->D, k, d_dist, d_idx);
   }
   EFFOCR_CUDA(cudaGetLastError());

@@ -116,10 +116,10 @@ class EffOCRPipeline:
         bottoms = [b[3] for b in char_b]
         return list(char_b), word_end_idx, rects, heights, bottoms
 
-    def infer_lines(self, images_rgb):
-        """images_rgb: list of u8 [H, W, 3] arrays -> list of dicts (text, nns, char_boxes, word_end_idx)."""
-        if len(images_rgb) == 0:
-            return []
+    # -- the two GPU phases as separately schedulable stages (run_effocr overlaps stage 1 of batch i+1 with stage 2 of batch i)
+    def stage_localize(self, images_rgb):
+        """Stage 1 on the CURRENT stream: upload the u8 lines once, letterbox + YOLOv5s + NMS on the device, boxes to
+        the host, reference box ordering / word ends / crop rectangles, rectangles back to the device."""
         packed_images = ops.pack_images(images_rgb)  # ONE upload of the u8 lines for both GPU phases
         dets = self.localize(images_rgb, packed_images)
         per_line, all_rects = [], []
@@ -128,13 +128,26 @@ class EffOCRPipeline:
             char_b, wei, rects, heights, bottoms = self._boxes_for_line(det, h, w)
             per_line.append((char_b, wei, heights, bottoms, len(rects)))
             all_rects += [(li,) + r for r in rects]
+        boxes, n = ops.pack_boxes(all_rects) if all_rects else (None, 0)
+        done = torch.cuda.current_stream().record_event()
+        return {"packed": packed_images, "per_line": per_line, "boxes": boxes, "n": n, "event": done}
+
+    def launch_recognize(self, st):
+        """Stage 2a on the CURRENT stream, asynchronous: crop -> encoder -> kNN for every character of the batch.
+        Returns the device id tensor (or None); nothing is synchronised."""
+        if not st["n"]:
+            return None
+        torch.cuda.current_stream().wait_event(st["event"])
+        _dist, idx, _ = self.recognizer.recognize_device(st["packed"][0], st["packed"][1], st["boxes"], st["n"], self.knn)
+        return idx
+
+    def finish_recognize(self, st, idx):
+        """Stage 2b: ids to the host (synchronises the current stream), decode + en_postprocess."""
         results = []
-        if all_rects:
-            boxes, n = ops.pack_boxes(all_rects)
-            dist, idx, _ = self.recognizer.recognize_device(packed_images[0], packed_images[1], boxes, n, self.knn)
+        if idx is not None:
             idx = idx.cpu().numpy()
         pos = 0
-        for (char_b, wei, heights, bottoms, n) in per_line:
+        for (char_b, wei, heights, bottoms, n) in st["per_line"]:
             if n == 0:
                 results.append({"text": None, "nns": [], "char_boxes": [], "word_end_idx": []})
                 continue
@@ -150,6 +163,45 @@ class EffOCRPipeline:
             results.append({"text": text, "nns": nns, "char_boxes": [b.tolist() for b in char_b], "word_end_idx": wei})
         return results
 
+    def stage_recognize(self, st):
+        return self.finish_recognize(st, self.launch_recognize(st))
+
+    def infer_lines(self, images_rgb):
+        """images_rgb: list of u8 [H, W, 3] arrays -> list of dicts (text, nns, char_boxes, word_end_idx)."""
+        if len(images_rgb) == 0:
+            return []
+        return self.stage_recognize(self.stage_localize(images_rgb))
+
+    def infer_batches(self, batches, overlap: bool = True):
+        """Yield the per-line results of each batch in order.  With overlap the reference's three barriered phases
+        become a software pipeline on ONE host thread: the recognizer kernels of batch i are enqueued without a
+        host synchronisation, then stage 1 of batch i+1 (pinned-memory packing, upload, letterbox, YOLOv5s, NMS, host
+        box logic) runs on a second CUDA stream while the GPU works through batch i, and only then are the ids of
+        batch i fetched and decoded.  (A worker thread was tried first: the two Python threads fought over the GIL
+        and the pipeline got slower.)  Results are identical to the sequential order: the stages share no mutable
+        state and every kernel is deterministic."""
+        batches = [b for b in batches]
+        if not overlap or len(batches) < 2:
+            for chunk in batches:
+                yield self.infer_lines(chunk)
+            return
+        side = getattr(self, "_side_stream", None)  # persistent: the caching allocator keeps one block pool per stream
+        if side is None:
+            side = self._side_stream = torch.cuda.Stream()
+
+        def stage1(chunk):
+            if len(chunk) == 0:
+                return None
+            with torch.cuda.stream(side):
+                return self.stage_localize(chunk)
+
+        st = stage1(batches[0])
+        for i in range(len(batches)):
+            idx = self.launch_recognize(st) if st is not None else None
+            st_next = stage1(batches[i + 1]) if i + 1 < len(batches) else None
+            yield self.finish_recognize(st, idx) if st is not None else []
+            st = st_next
+
 
 def run_effocr_sharded(images_rgb, pipeline, keys=None, batch_lines: int = 64, weights=None):
     """Data-parallel driver: every rank transcribes its shard of the lines, rank 0 gets the
@@ -164,12 +216,12 @@ def run_effocr_sharded(images_rgb, pipeline, keys=None, batch_lines: int = 64, w
     return D.gather_results(local)
 
 
-def run_effocr(images_rgb, pipeline: EffOCRPipeline, batch_lines: int = 64, keys=None):
+def run_effocr(images_rgb, pipeline: EffOCRPipeline, batch_lines: int = 64, keys=None, overlap: bool = True):
     """-> {key: text}; `keys` default to the line index.  Mirrors run_effocr's return (inference_results)."""
     keys = list(range(len(images_rgb))) if keys is None else list(keys)
     out = {}
-    for i0 in range(0, len(images_rgb), batch_lines):
-        res = pipeline.infer_lines(images_rgb[i0:i0 + batch_lines])
+    starts = list(range(0, len(images_rgb), batch_lines))
+    for i0, res in zip(starts, pipeline.infer_batches((images_rgb[i:i + batch_lines] for i in starts), overlap=overlap)):
         for k, r in zip(keys[i0:i0 + batch_lines], res):
             out[k] = r["text"]
     return out

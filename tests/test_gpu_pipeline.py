@@ -87,3 +87,17 @@ def test_run_effocr_returns_keyed_results():
     lines = [l[0] for l in synth.synthetic_lines(5, seed=2)]
     out = run_effocr(lines, pipe, batch_lines=2, keys=[f"l{i}.png" for i in range(5)])
     assert list(out) == [f"l{i}.png" for i in range(5)]
+
+
+def test_overlapped_pipeline_equals_sequential():
+    """The two-stage overlapped driver (stage 1 of batch i+1 on a side stream while stage 2 of batch i runs) returns
+    exactly what the sequential per-batch loop returns."""
+    from effocr_b200 import synth
+    pipe, *_ = _build(knn=2)
+    lines = [l[0] for l in synth.synthetic_lines(11, seed=21)]
+    batches = [lines[i:i + 3] for i in range(0, len(lines), 3)]
+    seq = [r for chunk in batches for r in pipe.infer_lines(chunk)]
+    ovl = [r for res in pipe.infer_batches(batches, overlap=True) for r in res]
+    assert len(seq) == len(ovl) == len(lines)
+    for a, b in zip(seq, ovl):
+        assert a["text"] == b["text"] and a["nns"] == b["nns"] and a["char_boxes"] == b["char_boxes"]
