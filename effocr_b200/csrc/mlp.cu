@@ -28,8 +28,37 @@ static int launch_mlp(const MlpArgs& a, cudaStream_t stream) {
   int pairs = sm_count() / 2;
   if (tiles < pairs) pairs = tiles;
   {
+    static const int cap = [] { const char* e = getenv("EFFOCR_MLP_MAX_PAIRS"); return e ? atoi(e) : 0; }();  // experiments only
+    if (cap > 0 && cap < pairs) pairs = cap;
+  }
+  {
     KernelScope ks(PROF_MLP_FUSED, stream);
     kern<<<2 * pairs, kMlpThreads, Cfg::kSmemBytes, stream>>>(ta, tw1, tw2, tx, a.M, a.HID, a.b1, a.b2, a.dbg);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
+template <int D>
+static int launch_mlp128(const MlpArgs& a, cudaStream_t stream) {
+  using Cfg = Mlp128Cfg<D>;
+  CUtensorMap ta, tw1, tw2, tx;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, a.h, a.M, D, a.ldh, 128));
+  EFFOCR_TRY(make_tmap_f16_2d(&tw1, a.w1, a.HID, D, D, 64));
+  EFFOCR_TRY(make_tmap_f16_2d(&tw2, a.w2, D, a.HID, a.HID, 96));
+  EFFOCR_TRY(make_tmap_2d(&tx, a.x, 4, a.M, D, a.ldx, 32, 32, 128));
+  auto kern = mlp_fused_pair128_kernel<D>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = (a.M + 255) / 256;
+  int pairs = sm_count() / 2;
+  if (tiles < pairs) pairs = tiles;
+  {
+    KernelScope ks(PROF_MLP_FUSED, stream);
+    kern<<<2 * pairs, kMlpThreads, Cfg::kSmemBytes, stream>>>(ta, tw1, tw2, tx, a.M, a.HID, a.b1, a.b2);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
@@ -43,6 +72,11 @@ int mlp_fused_f16(const MlpArgs& a, cudaStream_t stream) {
   if (a.ldh % 8 != 0 || a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.h) & 15) ||
       (reinterpret_cast<uintptr_t>(a.b1) & 15) || (reinterpret_cast<uintptr_t>(a.b2) & 15))
     return fail(EFFOCR_ERR_INVALID, "mlp_fused: operands must be 16-byte aligned with 16-byte multiple pitches");
+  static const int chunk = [] {
+    const char* e = getenv("EFFOCR_MLP_CHUNK");  // A/B: 64 = the first schedule (N = 64 fc1 MMAs, two S buffers), 128 (default)
+    return e ? atoi(e) : 128;
+  }();
+  if (chunk == 128 && a.D == 384 && !a.dbg) return launch_mlp128<384>(a, stream);
   static const int ahead = [] {
     const char* e = getenv("EFFOCR_MLP_AHEAD");  // A/B: 1 = fc1 one chunk ahead of fc2, 2 (default) = two chunks
     return e ? atoi(e) : 2;
