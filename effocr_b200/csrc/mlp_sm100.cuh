@@ -308,9 +308,12 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       // 32 x 32 fp32 boxes (128-byte rows, 4 KB) through the idle P buffers; the other eight only join the barrier.
       // The kernel's own clock64 timeline (tools/mlp_timeline.py) puts this drain at ~11 000 cycles per tile -- 18 B/clk
       // per SM, the L2 reduction rate with all CTAs draining together -- against ~1 800 cycles per hidden chunk in
-      // steady state (MMA-bound).  Tried and rejected: 16 warps x 2 KB boxes (12 300 cycles), prefetching the residual
-      // rows into L2 (no change: not an HBM-latency effect), residual add in registers with per-thread 64-byte row
-      // slices (43 000 cycles: 32 cache lines per load / store instruction).
+      // steady state (MMA-bound).  The rate does not depend on how many CTAs drain (4, 16 or 74 pairs: 9 700 / 9 200 /
+      // 10 300 cycles), i.e. it is the per-SM TMA reduction path.  Tried and rejected: 16 warps x 2 KB boxes (12 300
+      // cycles), prefetching the residual rows into L2 (no change), residual add in registers with per-thread 64-byte
+      // row slices (43 000 cycles: 32 cache lines per load / store instruction), residual add on the SM with the chunk
+      // transposed through shared memory so that every global access is a full 128-byte row segment (~17 000 cycles:
+      // eight warps of dependent TMEM-load / transpose / load / store steps).
       constexpr int OCH = D / 2 / 32;  // 32-column chunks per draining warp
       const int m_row0 = tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       if (warp_idx == 4 && lane == 0) MLP_DBG(6 * 64 + 0);
