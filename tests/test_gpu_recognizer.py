@@ -182,3 +182,21 @@ def test_knn_stress_config4_shape():
     dec = margin > 1e-6
     assert torch.equal(idx.cpu()[sub][dec], ri[dec])
     assert torch.allclose(dist.cpu()[sub], rd, atol=3e-6, rtol=0)
+
+
+def test_recognize_stream_equals_recognize_packed():
+    """The one-batch-in-flight streaming API returns, batch by batch, exactly what the synchronous call returns."""
+    import numpy as np
+    import torch
+    from effocr_b200 import synth
+    from effocr_b200.pipeline import PackedCrops, RecognizerPipeline
+    from oracle import vit as OV
+    sd = OV.randomize_affine(OV.init_vit_state_dict("vit_tiny_patch16_224", seed=0))
+    xb = torch.nn.functional.normalize(torch.randn(300, 192, generator=torch.Generator().manual_seed(3)), dim=1)
+    pipe = RecognizerPipeline(sd, xb, max_batch=64)
+    batches = [PackedCrops(synth.synthetic_crops(n, seed=s)[0]) for n, s in ((40, 1), (7, 2), (64, 3), (90, 4))]
+    ref = [pipe.recognize_packed(p, 5) for p in batches]
+    got = list(pipe.recognize_stream(iter(batches), 5))
+    assert len(got) == len(ref)
+    for (d0, i0), (d1, i1) in zip(ref, got):
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
