@@ -27,6 +27,7 @@ for src, dst in (("bench.json", f"{tag}_bench.json"), ("bench_reference.json", f
 
 def short(name: str) -> str:
     name = re.sub(r"^void ", "", name)
+    name = name.replace("effocr::", "")
     return re.sub(r"\(.*$", "", name)
 
 
@@ -84,8 +85,8 @@ def traffic_of(rep):
 
 traffic = {}
 if (G / "layer_full.ncu-rep").exists():
-    # tools/profile_gemm.py launch order: qkv, attention, proj, layernorm, fc1, fc2
-    order = ["gemm_qkv", "attention", "gemm_proj", "layernorm", "gemm_fc1_gelu", "gemm_fc2"]
+    # tools/profile_gemm.py launch order: qkv, attention, proj, layernorm, fused MLP block
+    order = ["gemm_qkv", "attention", "gemm_proj", "layernorm", "mlp_fused"]
     for name, (_, t) in zip(order, traffic_of("layer_full.ncu-rep")):
         traffic[name] = t
 if (G / "misc_full.ncu-rep").exists():

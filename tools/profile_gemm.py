@@ -1,4 +1,5 @@
-"""ncu target: the four ViT-S GEMM shapes at batch 1024 (M = 201728), attention and LayerNorm, one launch each after warm-up."""
+"""ncu target: one ViT-S layer at batch 1024 (M = 201728): QKV GEMM, attention, proj GEMM, LayerNorm, fused MLP block;
+one launch each after warm-up."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -24,7 +25,6 @@ for _ in range(reps):
     ops.attention(qkv, 1024, 6)
     ops.gemm(h, wproj, bias=b384, out_dtype=torch.float32, resid=x, out=x)
     ops.layernorm(x, g, b384)
-    ops.gemm(h, wfc1, bias=b1536, act=1, out=o1536)
-    ops.gemm(mid, wfc2, bias=b384, out_dtype=torch.float32, resid=x, out=x)
+    ops.mlp_fused(x, h, wfc1, b1536, wfc2, b384)  # fc1 + GELU + fc2 + residual in one kernel
 torch.cuda.synchronize()
 print("done")
