@@ -208,6 +208,7 @@ def kernel_work(tag: str, B: int, D: int, mlp: int, n_index: int):
         "knn_gemm_topk": 2.0 * B * n_index * D * 3,  # three fp16 partial products per fp32 product
     }
     bytes_ = {
+        "proj_ln": M * D * (2 + 4 + 4 + 2),  # att in, x in, x out, h out (fused projection + residual + LayerNorm)
         "layernorm": M * D * (4 + 2),
         "crop_resize": B * (64 * 29 * 3 + 3 * 224 * 224 * 2),
         "final_layernorm": B * D * 8,

@@ -43,6 +43,8 @@ SIGNATURES = {
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "effocr_mlp_fused_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
                                      c_int, c_void_p]),
+    "effocr_proj_ln_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p,
+                                   c_ll, c_int, c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -21,4 +21,22 @@ bool mlp_fused_supported(int D, int HID);
 // x += GELU(h . w1^T + b1) . w2^T + b2
 int mlp_fused_f16(const MlpArgs& a, cudaStream_t stream);
 
+struct ProjLnArgs {
+  const __half* att = nullptr;  // [M, D] attention output, leading dimension lda
+  long long lda = 0;
+  const __half* w = nullptr;    // [D, D] projection weight (torch Linear layout)
+  const float* bias = nullptr;  // [D]
+  float* x = nullptr;           // [M, D] fp32 residual stream, updated in place
+  long long ldx = 0;
+  const float *gamma = nullptr, *beta = nullptr;  // LayerNorm affine [D]
+  float eps = 1e-6f;
+  __half* h = nullptr;          // [M, D] LayerNorm(x) out
+  long long ldh = 0;
+  int M = 0, D = 0;
+};
+
+bool proj_ln_supported(int D);
+// x += att . w^T + bias;  h = LayerNorm(x) * gamma + beta   (one kernel, full-row tiles)
+int proj_ln_f16(const ProjLnArgs& a, cudaStream_t stream);
+
 }  // namespace effocr

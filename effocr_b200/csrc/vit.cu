@@ -156,6 +156,11 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     return !(e && e[0] == '0');
   }();
   const bool fused_mlp = fused_env && mlp_fused_supported(D, v->mlp);
+  static const bool pln_env = [] {
+    const char* e = getenv("EFFOCR_PROJ_LN");  // "0" = separate projection GEMM + LayerNorm kernels (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  const bool fused_pln = pln_env && proj_ln_supported(D);
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
@@ -164,11 +169,18 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
     EFFOCR_TRY(gemm_f16(g, s));
     EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
-    g = GemmArgs();
-    g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
-    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
-    EFFOCR_TRY(gemm_f16(g, s));
-    EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
+    if (fused_pln) {  // projection + residual + norm2 in one full-row kernel: x is read and written once, no L2 reductions
+      ProjLnArgs p;
+      p.att = v->att; p.lda = D; p.w = L.w_proj; p.bias = L.b_proj; p.x = v->x; p.ldx = D;
+      p.gamma = L.ln2_w; p.beta = L.ln2_b; p.eps = v->eps; p.h = v->h16; p.ldh = D; p.M = M; p.D = D;
+      EFFOCR_TRY(proj_ln_f16(p, s));
+    } else {
+      g = GemmArgs();
+      g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
+      g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
+      EFFOCR_TRY(gemm_f16(g, s));
+      EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
+    }
     if (fused_mlp) {  // fc1 + GELU + fc2 + residual in one kernel: the [M, mlp] hidden activations never reach HBM
       MlpArgs m;
       m.h = v->h16; m.ldh = D; m.w1 = L.w_fc1; m.b1 = L.b_fc1; m.w2 = L.w_fc2; m.b2 = L.b_fc2;

@@ -67,6 +67,24 @@ def mlp_fused(x: torch.Tensor, h: torch.Tensor, w1: torch.Tensor, b1: torch.Tens
     return x
 
 
+def proj_ln(x: torch.Tensor, att: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+            eps: float = 1e-6, out=None) -> torch.Tensor:
+    """x += att @ w.T + bias (in place, fp32);  returns LayerNorm(x) * gamma + beta as fp16 -- one fused tcgen05 kernel."""
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x")
+    att = _cuda(att, torch.float16, "att")
+    w = _cuda(w, torch.float16, "w")
+    M, D = x.shape
+    assert att.shape == (M, D) and w.shape == (D, D) and w.is_contiguous() and x.stride(1) == 1 and att.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, D), device=x.device, dtype=torch.float16)
+    _lib.check(lib.effocr_proj_ln_f16(att.data_ptr(), att.stride(0), w.data_ptr(), _cuda(bias, torch.float32, "bias").data_ptr(),
+                                      x.data_ptr(), x.stride(0), _cuda(gamma, torch.float32, "gamma").data_ptr(),
+                                      _cuda(beta, torch.float32, "beta").data_ptr(), float(eps), out.data_ptr(), out.stride(0),
+                                      M, D, _lib.stream_ptr()), "effocr_proj_ln_f16")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
               out_dtype=torch.float16) -> torch.Tensor:
     lib = _lib.load()

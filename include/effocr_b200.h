@@ -75,6 +75,14 @@ EFFOCR_API int effocr_gemm_f16(const void* d_A, long long lda, const void* d_W, 
 EFFOCR_API int effocr_mlp_fused_f16(const void* d_h, long long ldh, const void* d_w1, const float* d_b1, const void* d_w2,
                          const float* d_b2, float* d_x, long long ldx, int M, int D, int HID, void* stream);
 
+/* ---- fused attention projection + residual + LayerNorm (tcgen05, CTA pairs, full-row tiles) ------
+ * x[M,D] += att[M,D] . Wp[D,D]^T + bp;   h[M,D] = LayerNorm(x) * gamma + beta (fp16).
+ * The `x = x + attn(...)` tail and the `norm2` of timm Block.forward (un-vendored; models/encoders.py:58,62-64) in
+ * one kernel: no L2 reductions, x is read and written once.  D = 384. */
+EFFOCR_API int effocr_proj_ln_f16(const void* d_att, long long lda, const void* d_w, const float* d_bias, float* d_x,
+                       long long ldx, const float* d_gamma, const float* d_beta, float eps, void* d_h, long long ldh,
+                       int M, int D, void* stream);
+
 /* ---- K1: fused crop -> square white pad -> AA bilinear 224x224 -> normalise -------------------
  * Replaces the numpy slice + `create_paired_transform` per-crop CPU path
  * (infer_effocr.py:284-293, infer_effocr_onnx_multi.py:307-340, utils/datasets_utils.py:69-90,166-172).

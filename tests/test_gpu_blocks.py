@@ -133,3 +133,28 @@ def test_mlp_fused(M, D, HID):
     ops.gemm(mid.contiguous(), w2, bias=b2, out_dtype=torch.float32, resid=y, out=y)
     assert _rel(x - x0, y - x0) < 1e-4
     assert torch.isfinite(x).all()
+
+
+@pytest.mark.parametrize("M", [100, 256, 5000, 70001])
+def test_proj_ln_fused(M):
+    """x += att Wp^T + bp and h = LayerNorm(x) in ONE full-row kernel vs fp32 torch and vs the unfused kernels."""
+    from effocr_b200 import ops
+    D = 384
+    torch.manual_seed(0)
+    att = (torch.randn(M, D, device="cuda") * 0.7).half()
+    w = (torch.randn(D, D, device="cuda") * 0.05).half()
+    b = torch.randn(D, device="cuda") * 0.3
+    g = 1.0 + 0.2 * torch.randn(D, device="cuda")
+    be = 0.2 * torch.randn(D, device="cuda")
+    x0 = torch.randn(M, D, device="cuda") * 2.0 + 0.5
+    x = x0.clone()
+    h = ops.proj_ln(x, att, w, b, g, be)
+    xr = x0 + (att.float() @ w.float().t() + b)
+    hr = torch.nn.functional.layer_norm(xr, (D,), g, be, 1e-6)
+    assert _rel(x, xr) < 2e-6          # fp32 accumulation-order noise only
+    assert _rel(h, hr) < 4e-4          # fp16 output rounding
+    y = x0.clone()
+    ops.gemm(att, w, bias=b, out_dtype=torch.float32, resid=y, out=y)
+    hu = ops.layernorm(y, g, be)
+    assert _rel(x, y) < 1e-6 and _rel(h, hu) < 3e-4
+    assert torch.isfinite(h.float()).all()
