@@ -38,7 +38,11 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 MODEL = "vit_small_patch16_224"
-VIT_S_FLOPS_PER_CROP = 9_196_996_608  # SURVEY.md section 8d (matmul/conv FLOPs only)
+VIT_S_FLOPS_PER_CROP = 9_196_996_608  # SURVEY.md section 8d (matmul/conv FLOPs only): what timm computes per crop
+# The engine runs the LAST block's attention / projection / MLP for the class token only (timm pools x[:, 0]; the other
+# 196 rows of that block cannot reach the embedding): 196 * (2*384*384 + 4*1536*384) + 4*196*197*384 FLOPs less per crop.
+VIT_S_FLOPS_EXECUTED_PER_CROP = VIT_S_FLOPS_PER_CROP - (196 * (2 * 384 * 384 + 4 * 1536 * 384) + 4 * 196 * 197 * 384)
+LAST_BLOCK_TAGS = ("mlp_fused", "proj_ln", "gemm_proj", "gemm_fc1_gelu", "gemm_fc2", "attention")
 
 
 def parse():
@@ -432,7 +436,18 @@ def main():
         dom = max(prof.items(), key=lambda kv: kv[1][1])
         dom_tag, (dom_cnt, dom_ms) = dom
         bound, work = kernel_work(dom_tag, B, D, mlp, args.index)
-        avg_ms = dom_ms / dom_cnt
+
+        def eff_launches(tag, cnt):
+            """Launches per step weighted by their size: the last block's launch covers 1 of 197 rows per crop."""
+            n = cnt / prof_steps
+            if tag in LAST_BLOCK_TAGS and n > 1:
+                return n - 1 + 1.0 / 197
+            if tag == "layernorm" and "proj_ln" not in prof and n > 1:
+                return n - 1 + 1.0 / 197
+            return n
+
+        n_eff = eff_launches(dom_tag, dom_cnt)
+        avg_ms = dom_ms / prof_steps / n_eff  # time per FULL-SIZE launch
         traffic = None
         try:
             traffic = json.loads((ROOT / "profiles" / "roofline_traffic.json").read_text()).get(dom_tag)
@@ -450,17 +465,18 @@ def main():
             peak_src = "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         roofline = {"kernel": dom_tag, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                    "avg_launch_ms": avg_ms, "launches_per_step": dom_cnt / prof_steps,
+                    "avg_launch_ms": avg_ms, "launches_per_step": dom_cnt / prof_steps, "full_size_launches_per_step": n_eff,
                     "share_of_step": dom_ms / prof_steps / step_ms if step_ms else None}
         kernels = {}
         for tag, (cnt, tot) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
             b, w = kernel_work(tag, B, D, mlp, args.index)
             ent = {"launches_per_step": cnt / prof_steps, "ms_per_step": tot / prof_steps,
                    "share": tot / prof_steps / step_ms if step_ms else None}
+            ne = eff_launches(tag, cnt)
             if b == "tensor":
-                ent["tflops"] = w / (tot / cnt / 1e3) / 1e12
+                ent["tflops"] = w * ne / (tot / prof_steps / 1e3) / 1e12
             elif b == "hbm":
-                ent["gbs"] = w / (tot / cnt / 1e3) / 1e9
+                ent["gbs"] = w * ne / (tot / prof_steps / 1e3) / 1e9
             kernels[tag] = ent
 
         cpu_block = None
@@ -495,7 +511,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": roofline,
-            "tensor_frac_whole_step": (VIT_S_FLOPS_PER_CROP * B / (ms_dev / args.steps / 1e3) / 1e12) / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+            "tensor_frac_whole_step": (VIT_S_FLOPS_EXECUTED_PER_CROP * B / (ms_dev / args.steps / 1e3) / 1e12) / float(peaks.get("bf16_tflops_sustained", 1400.0)),
+            "flops_per_crop": {"reference_model": VIT_S_FLOPS_PER_CROP, "executed": VIT_S_FLOPS_EXECUTED_PER_CROP,
+                               "note": "last block runs for the class token only (the pooled token); outputs unchanged"},
             "kernels": kernels,
         }
         if cpu_block is not None:

@@ -161,40 +161,68 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     return !(e && e[0] == '0');
   }();
   const bool fused_pln = pln_env && proj_ln_supported(D);
+  static const bool cls_env = [] {
+    const char* e = getenv("EFFOCR_VIT_LAST_BLOCK_FULL");  // "1" = run the last block on all 197 tokens (A/B runs)
+    return !(e && e[0] == '1');
+  }();
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
-    g = GemmArgs();
-    g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
-    g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
-    EFFOCR_TRY(gemm_f16(g, s));
-    EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
+    if (cls_env && l == v->depth - 1) {
+      // last block: K and V for every token, Q for the class tokens only (see below)
+      g = GemmArgs();
+      g.A = v->h16; g.lda = D; g.W = L.w_qkv + static_cast<size_t>(D) * D; g.ldw = D; g.M = M; g.N = 2 * D; g.K = D;
+      g.out = v->qkv + D; g.ldo = 3 * D; g.bias = L.b_qkv + D; g.prof_tag = PROF_GEMM_QKV;
+      EFFOCR_TRY(gemm_f16(g, s));
+      g = GemmArgs();
+      g.A = v->h16; g.lda = static_cast<long long>(T) * D; g.W = L.w_qkv; g.ldw = D; g.M = B; g.N = D; g.K = D;
+      g.out = v->qkv; g.ldo = static_cast<long long>(T) * 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_OTHER;
+      EFFOCR_TRY(gemm_f16(g, s));
+    } else {
+      g = GemmArgs();
+      g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
+      g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
+      EFFOCR_TRY(gemm_f16(g, s));
+    }
+    // Last block: only the class token reaches the embedding (timm pools x[:, 0]), so the rows of the 196 patch tokens
+    // are dead after K and V have been formed: CLS-query attention, then projection / norm2 / MLP on the B class rows
+    // of x only (row pitch T * D).  Same kernels, same per-row arithmetic; 1/12 of the projection and MLP work goes away.
+    const bool cls_only = cls_env && l == v->depth - 1;
+    const int Mr = cls_only ? B : M;                                   // rows that continue through this block
+    const long long ldx = cls_only ? static_cast<long long>(T) * D : D;  // pitch of those rows in x
+    if (cls_only) {
+      KernelScope ks(PROF_ATTENTION, s);
+      cls_attention_kernel<<<(B * v->H + 3) / 4, 128, 0, s>>>(v->qkv, v->att, B, T, v->H, 0.125f);
+      EFFOCR_CUDA(cudaGetLastError());
+    } else {
+      EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
+    }
     if (fused_pln) {  // projection + residual + norm2 in one full-row kernel: x is read and written once, no L2 reductions
       ProjLnArgs p;
-      p.att = v->att; p.lda = D; p.w = L.w_proj; p.bias = L.b_proj; p.x = v->x; p.ldx = D;
-      p.gamma = L.ln2_w; p.beta = L.ln2_b; p.eps = v->eps; p.h = v->h16; p.ldh = D; p.M = M; p.D = D;
+      p.att = v->att; p.lda = D; p.w = L.w_proj; p.bias = L.b_proj; p.x = v->x; p.ldx = ldx;
+      p.gamma = L.ln2_w; p.beta = L.ln2_b; p.eps = v->eps; p.h = v->h16; p.ldh = D; p.M = Mr; p.D = D;
       EFFOCR_TRY(proj_ln_f16(p, s));
     } else {
       g = GemmArgs();
-      g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = M; g.N = D; g.K = D;
-      g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_PROJ;
+      g.A = v->att; g.lda = D; g.W = L.w_proj; g.ldw = D; g.M = Mr; g.N = D; g.K = D;
+      g.out = v->x; g.ldo = ldx; g.out_f32 = 1; g.bias = L.b_proj; g.resid = v->x; g.ldr = ldx; g.prof_tag = PROF_GEMM_PROJ;
       EFFOCR_TRY(gemm_f16(g, s));
-      EFFOCR_TRY(layernorm_f16(v->x, D, L.ln2_w, L.ln2_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
+      EFFOCR_TRY(layernorm_f16(v->x, ldx, L.ln2_w, L.ln2_b, v->h16, D, Mr, D, v->eps, s, PROF_LAYERNORM));
     }
     if (fused_mlp) {  // fc1 + GELU + fc2 + residual in one kernel: the [M, mlp] hidden activations never reach HBM
       MlpArgs m;
       m.h = v->h16; m.ldh = D; m.w1 = L.w_fc1; m.b1 = L.b_fc1; m.w2 = L.w_fc2; m.b2 = L.b_fc2;
-      m.x = v->x; m.ldx = D; m.M = M; m.D = D; m.HID = v->mlp;
+      m.x = v->x; m.ldx = ldx; m.M = Mr; m.D = D; m.HID = v->mlp;
       EFFOCR_TRY(mlp_fused_f16(m, s));
       continue;
     }
     g = GemmArgs();
-    g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = M; g.N = v->mlp; g.K = D;
+    g.A = v->h16; g.lda = D; g.W = L.w_fc1; g.ldw = D; g.M = Mr; g.N = v->mlp; g.K = D;
     g.out = v->mid; g.ldo = v->mlp; g.bias = L.b_fc1; g.act = 1; g.prof_tag = PROF_GEMM_FC1;
     EFFOCR_TRY(gemm_f16(g, s));
     g = GemmArgs();
-    g.A = v->mid; g.lda = v->mlp; g.W = L.w_fc2; g.ldw = v->mlp; g.M = M; g.N = D; g.K = v->mlp;
-    g.out = v->x; g.ldo = D; g.out_f32 = 1; g.bias = L.b_fc2; g.resid = v->x; g.ldr = D; g.prof_tag = PROF_GEMM_FC2;
+    g.A = v->mid; g.lda = v->mlp; g.W = L.w_fc2; g.ldw = v->mlp; g.M = Mr; g.N = D; g.K = v->mlp;
+    g.out = v->x; g.ldo = ldx; g.out_f32 = 1; g.bias = L.b_fc2; g.resid = v->x; g.ldr = ldx; g.prof_tag = PROF_GEMM_FC2;
     EFFOCR_TRY(gemm_f16(g, s));
   }
   // final LayerNorm on the CLS rows only (row stride T * D)

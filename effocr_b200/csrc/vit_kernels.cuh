@@ -103,6 +103,85 @@ __global__ void __launch_bounds__(256) im2patch_kernel(const float* __restrict__
   }
 }
 
+// Attention for the CLS query only (last encoder block).  timm's ViT with num_classes = 0 pools the class token
+// (`x[:, 0]` after the final norm; models/encoders.py:58 -> timm VisionTransformer.forward_head), so nothing the last
+// block computes for the 196 patch tokens can reach the embedding: their queries, their attention rows, their
+// projection and their MLP are dead.  K and V of ALL tokens are still needed.  One warp per (image, head): lane = key
+// for the scores (fp32, exact softmax -- P is not rounded to fp16 here), lane = output dim pair for P.V.
+__global__ void __launch_bounds__(128) cls_attention_kernel(const __half* __restrict__ qkv, __half* __restrict__ out, int batch,
+                                                            int T, int H, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (bh >= batch * H) return;
+  const int b = bh / H, h = bh % H;
+  const int D = H * 64;
+  const __half* base = qkv + static_cast<long long>(b) * T * 3 * D;
+  float q[64];
+  {
+    const uint4* qp = reinterpret_cast<const uint4*>(base + h * 64);  // token 0
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 u = __ldg(qp + i);
+      const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __half22float2(hp[t]);
+        q[8 * i + 2 * t] = f.x;
+        q[8 * i + 2 * t + 1] = f.y;
+      }
+    }
+  }
+  float sc[7];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int it = 0; it < 7; ++it) {
+    const int t = it * 32 + lane;
+    float a = -INFINITY;
+    if (t < T) {
+      const uint4* kp = reinterpret_cast<const uint4*>(base + static_cast<long long>(t) * 3 * D + D + h * 64);
+      a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = __ldg(kp + i);
+        const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt) {
+          const float2 f = __half22float2(hp[tt]);
+          a = fmaf(q[8 * i + 2 * tt], f.x, a);
+          a = fmaf(q[8 * i + 2 * tt + 1], f.y, a);
+        }
+      }
+      a *= scale;
+    }
+    sc[it] = a;
+    mx = fmaxf(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int it = 0; it < 7; ++it) {
+    sc[it] = (it * 32 + lane < T) ? __expf(sc[it] - mx) : 0.f;
+    sum += sc[it];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.0f / sum;
+  float o0 = 0.f, o1 = 0.f;  // output dims 2*lane, 2*lane + 1
+  const __half* vbase = base + 2 * D + h * 64 + 2 * lane;
+#pragma unroll
+  for (int it = 0; it < 7; ++it) {
+    const int nt = (T - it * 32) < 32 ? (T - it * 32) : 32;
+    for (int j = 0; j < nt; ++j) {
+      const float p = __shfl_sync(0xffffffffu, sc[it], j);
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vbase + static_cast<long long>(it * 32 + j) * 3 * D));
+      o0 = fmaf(p, f.x, o0);
+      o1 = fmaf(p, f.y, o1);
+    }
+  }
+  *reinterpret_cast<__half2*>(out + static_cast<long long>(b) * D + h * 64 + 2 * lane) = __floats2half2_rn(o0 * inv, o1 * inv);
+}
+
 // x[b * T + 0, :] = cls + pos[0, :]
 __global__ void cls_pos_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                int batch, int T, int D) {
