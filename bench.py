@@ -40,8 +40,9 @@ sys.path.insert(0, str(ROOT))
 MODEL = "vit_small_patch16_224"
 VIT_S_FLOPS_PER_CROP = 9_196_996_608  # SURVEY.md section 8d (matmul/conv FLOPs only): what timm computes per crop
 # The engine runs the LAST block's attention / projection / MLP for the class token only (timm pools x[:, 0]; the other
-# 196 rows of that block cannot reach the embedding): 196 * (2*384*384 + 4*1536*384) + 4*196*197*384 FLOPs less per crop.
-VIT_S_FLOPS_EXECUTED_PER_CROP = VIT_S_FLOPS_PER_CROP - (196 * (2 * 384 * 384 + 4 * 1536 * 384) + 4 * 196 * 197 * 384)
+# 196 rows of that block cannot reach the embedding): 196 * (proj 2*384*384 + MLP 4*1536*384 + Q 2*384*384) + attention
+# 4*196*197*384 FLOPs less per crop.
+VIT_S_FLOPS_EXECUTED_PER_CROP = VIT_S_FLOPS_PER_CROP - (196 * (2 * 384 * 384 + 4 * 1536 * 384 + 2 * 384 * 384) + 4 * 196 * 197 * 384)
 LAST_BLOCK_TAGS = ("mlp_fused", "proj_ln", "gemm_proj", "gemm_fc1_gelu", "gemm_fc2", "attention")
 
 
@@ -444,6 +445,8 @@ def main():
                 return n - 1 + 1.0 / 197
             if tag == "layernorm" and "proj_ln" not in prof and n > 1:
                 return n - 1 + 1.0 / 197
+            if tag == "gemm_qkv" and n > 1:
+                return n - 1 + 2.0 / 3  # last block: K and V for all tokens, Q for the class rows only
             return n
 
         n_eff = eff_launches(dom_tag, dom_cnt)
