@@ -100,6 +100,29 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int esz, uint64_t rows, uin
   return EFFOCR_OK;
 }
 
+// 4-D tensor map over an NHWC-like tensor: dims / box / traversal strides innermost first; byte strides of dims 1..3.
+int make_tmap_4d(CUtensorMap* out, const void* base, int esz, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4], const uint32_t elem_strides[4], int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(EFFOCR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(EFFOCR_ERR_INVALID, "TMA operand must be 16-byte aligned");
+  for (int i = 0; i < 3; ++i)
+    if (strides_bytes[i] % 16 != 0) return fail(EFFOCR_ERR_INVALID, "TMA strides must be multiples of 16 bytes");
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+  if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+  else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+  else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  cuuint64_t d[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t st[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {elem_strides[0], elem_strides[1], elem_strides[2], elem_strides[3]};
+  CUresult r = enc(out, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                   const_cast<void*>(base), d, st, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EFFOCR_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed with CUresult " + std::to_string(int(r)));
+  return EFFOCR_OK;
+}
+
 // ------------------------------------------------------------------ launch accounting / profiling
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_prof_on{0};

@@ -62,4 +62,9 @@ int make_tmap_f16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
 int make_tmap_2d(CUtensorMap* out, const void* base, int esz, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes);
 
+// 4-D tiled tensor map (innermost dimension first), e.g. NHWC activations as {C, W, H, N}; elem_strides are the TMA
+// traversal strides (a box of box[i] positions loads ceil(box[i] / elem_strides[i]) elements along dimension i).
+int make_tmap_4d(CUtensorMap* out, const void* base, int esz, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                 const uint32_t box[4], const uint32_t elem_strides[4], int swizzle_bytes);
+
 }  // namespace effocr

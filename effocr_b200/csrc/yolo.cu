@@ -17,6 +17,7 @@
 
 #include "../../include/effocr_b200.h"
 #include "gemm.h"
+#include "conv3_sm100.cuh"
 
 namespace effocr {
 
@@ -368,6 +369,45 @@ static inline int grid_for(long long total) {
   return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+template <int BN, int CB>
+static int launch_conv3(const __half* in, int ld_in, int B, int H, int W, int C, const __half* w, int kdim, const float* bias,
+                        int Cout, int stride, __half* out, int ld_out, const __half* resid, int ld_res, cudaStream_t s) {
+  using Cfg = Conv3Cfg<BN, CB>;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  CUtensorMap tin, tw, tout;
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
+    const uint64_t st[3] = {static_cast<uint64_t>(ld_in) * 2, static_cast<uint64_t>(W) * ld_in * 2, static_cast<uint64_t>(H) * W * ld_in * 2};
+    const uint32_t box[4] = {CB, static_cast<uint32_t>(kConvTW * stride), static_cast<uint32_t>(kConvTH * stride), 1};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    EFFOCR_TRY(make_tmap_4d(&tin, in, 2, dims, st, box, es, CB * 2));
+  }
+  EFFOCR_TRY(make_tmap_2d(&tw, w, 2, Cout, kdim, kdim, BN, CB, CB * 2));
+  {
+    const uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
+    const uint64_t st[3] = {static_cast<uint64_t>(ld_out) * 2, static_cast<uint64_t>(Wo) * ld_out * 2, static_cast<uint64_t>(Ho) * Wo * ld_out * 2};
+    const uint32_t box[4] = {32, kConvTW, 2, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    EFFOCR_TRY(make_tmap_4d(&tout, out, 2, dims, st, box, es, 64));
+  }
+  auto kern = conv3_tc_kernel<BN, CB>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  Conv3Params p;
+  p.B = B; p.Ho = Ho; p.Wo = Wo; p.C = C; p.Cout = Cout; p.stride = stride; p.bias = bias; p.resid = resid; p.ld_res = ld_res;
+  const int tiles = B * ((Ho + kConvTH - 1) / kConvTH) * ((Wo + kConvTW - 1) / kConvTW) * ((Cout + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  {
+    KernelScope ks(PROF_GEMM_OTHER, s);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tin, tw, tout, p);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
 struct YoloRun {
   YoloHandle* h;
   cudaStream_t s;
@@ -405,6 +445,19 @@ struct YoloRun {
     if (status) return;
     const int Ho = (H - 1) / cw.s + 1, Wo = (W - 1) / cw.s + 1;
     const long long rows = static_cast<long long>(B) * Ho * Wo;
+    static const bool use_im2col = [] {
+      const char* e = getenv("EFFOCR_YOLO_CONV3");  // "im2col" = explicit gather + GEMM (first version; A/B runs)
+      return e && e[0] == 'i';
+    }();
+    if (!use_im2col) {  // implicit GEMM: the A operand comes straight from the activation tensor through 4-D TMA boxes
+      const __half* rp = resid ? resid->p : nullptr;
+      const int rl = resid ? resid->ld : 0;
+      if (cw.cin == 32) status = launch_conv3<64, 32>(in.p, in.ld, B, H, W, cw.cin, cw.w, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s);
+      else if (cw.cout <= 64) status = launch_conv3<64, 64>(in.p, in.ld, B, H, W, cw.cin, cw.w, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s);
+      else if (cw.cout <= 128) status = launch_conv3<128, 64>(in.p, in.ld, B, H, W, cw.cin, cw.w, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s);
+      else status = launch_conv3<256, 64>(in.p, in.ld, B, H, W, cw.cin, cw.w, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s);
+      return;
+    }
     if (static_cast<size_t>(rows) * cw.kdim > h->col_elems) { status = fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small"); return; }
     {
       KernelScope ks(PROF_CONV_IM2COL, s);
