@@ -73,7 +73,7 @@ __device__ __forceinline__ void mma_m16n8k16_f16f32(float (&c)[4], const uint32_
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 2) yolo_stem_kernel(const float* __restrict__ img, const __half* __restrict__ w /*[32,112]*/,
+__global__ void __launch_bounds__(256) yolo_stem_kernel(const float* __restrict__ img, const __half* __restrict__ w /*[32,112]*/,
                                                         const float* __restrict__ bias, __half* __restrict__ out, int ld_out,
                                                         int B, int H, int W) {
   __shared__ __align__(16) __half patch[3 * kStemPlane];
@@ -110,19 +110,37 @@ __global__ void __launch_bounds__(256, 2) yolo_stem_kernel(const float* __restri
     bv[nt][1] = bias[nt * 8 + 2 * t + 1];
   }
 
+  // software pipeline: the NEXT tile's input patch is fetched into registers (16 values per thread) while the current
+  // tile is being multiplied, so the global-load latency is off the load -> sync -> compute -> sync chain
+  constexpr int kPerThread = (3 * kStemPlane + 255) / 256;  // 16
+  float pre[kPerThread];
+  auto fetch = [&](int tile) {
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int iy0 = 2 * ty * kStemTH - 2, ix0 = 2 * tx * kStemTW - 2;
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int i = threadIdx.x + u * 256;
+      float v = 0.f;
+      if (i < 3 * kStemPlane) {
+        const int c = i / kStemPlane, r = (i % kStemPlane) / kStemPW, x = i % kStemPW;
+        const int iy = iy0 + r, ix = ix0 + x;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
+      }
+      pre[u] = v;
+    }
+  };
+  if (blockIdx.x < num_tiles) fetch(blockIdx.x);
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
     const int oy0 = ty * kStemTH, ox0 = tx * kStemTW;
-    const int iy0 = 2 * oy0 - 2, ix0 = 2 * ox0 - 2;
     __syncthreads();  // previous tile's readers are done with the patch
-    for (int i = threadIdx.x; i < 3 * kStemPlane; i += 256) {
-      const int c = i / kStemPlane, r = (i % kStemPlane) / kStemPW, x = i % kStemPW;
-      const int iy = iy0 + r, ix = ix0 + x;
-      float v = 0.f;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(img + ((static_cast<long long>(b) * 3 + c) * H + iy) * W + ix);
-      patch[i] = __float2half_rn(v);
+#pragma unroll
+    for (int u = 0; u < kPerThread; ++u) {
+      const int i = threadIdx.x + u * 256;
+      if (i < 3 * kStemPlane) patch[i] = __float2half_rn(pre[u]);
     }
     __syncthreads();
+    if (tile + gridDim.x < num_tiles) fetch(tile + gridDim.x);
     const int oy = oy0 + warp;  // this warp's output row
     float acc[2][4][4];
 #pragma unroll
@@ -532,7 +550,7 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
       r.gemm(h->col, 112, p1, cw, x0, nullptr);
     } else {
       const int tiles = B * ((H1 + kStemTH - 1) / kStemTH) * ((W1 + kStemTW - 1) / kStemTW);
-      const int grid = tiles < 148 * 2 ? tiles : 148 * 2;  // persistent, 2 CTAs per SM (128 registers)
+      const int grid = tiles < sm_count() ? tiles : sm_count();  // persistent, one CTA per SM (222 registers: B fragments + prefetch)
       KernelScope ks(PROF_YOLO_MISC, s);
       yolo_stem_kernel<<<grid, 256, 0, s>>>(img, cw.w, cw.b, x0.p, x0.ld, B, H, W);
       EFFOCR_CUDA(cudaGetLastError());
