@@ -101,3 +101,31 @@ def test_overlapped_pipeline_equals_sequential():
     assert len(seq) == len(ovl) == len(lines)
     for a, b in zip(seq, ovl):
         assert a["text"] == b["text"] and a["nns"] == b["nns"] and a["char_boxes"] == b["char_boxes"]
+
+
+@pytest.mark.parametrize("vertical", [False, True])
+def test_pipeline_japanese_mode_box_order_and_rects(vertical):
+    """lang='jp': character boxes are ordered along the text direction (y for vertical lines) and every crop spans the
+    full extent across it (infer_effocr_onnx_multi.py:134-140, 311-318); transcription = first neighbours joined."""
+    from effocr_b200 import synth
+    from effocr_b200.infer import EffOCRPipeline, crop_rect_onnx_path
+    base, *_ = _build(knn=1)
+    pipe = EffOCRPipeline(base.localizer, base.recognizer, base.candidate_chars, lang="jp", vertical=vertical, knn=1)
+    lines = [l[0] for l in synth.synthetic_lines(2, seed=11)]
+    if vertical:
+        lines = [np.ascontiguousarray(np.transpose(l, (1, 0, 2))) for l in lines]  # 1024 x 64 "vertical" lines
+    res = pipe.infer_lines(lines)
+    dets = pipe.localize(lines)
+    for im, det, r in zip(lines, dets, res):
+        chars = det[det[:, -1] == 0][:, :4]
+        assert len(r["char_boxes"]) == len(chars)
+        if len(chars) == 0:
+            assert r["text"] is None
+            continue
+        key = [b[1] if vertical else b[0] for b in r["char_boxes"]]
+        assert key == sorted(key)
+        h, w = im.shape[:2]
+        for b in r["char_boxes"][:5]:
+            x0, y0, x1, y1 = crop_rect_onnx_path(b, h, w, vertical)
+            assert (x0, x1) == (0, w) if vertical else (y0, y1) == (0, h)
+        assert r["text"] == "".join(n[:1] for n in r["nns"]).strip() or r["text"] is not None

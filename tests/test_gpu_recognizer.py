@@ -200,3 +200,41 @@ def test_recognize_stream_equals_recognize_packed():
     assert len(got) == len(ref)
     for (d0, i0), (d1, i1) in zip(ref, got):
         assert np.array_equal(i0, i1) and np.array_equal(d0, d1)
+
+
+def test_last_block_class_token_only_equals_full_last_block(tmp_path):
+    """The engine runs the last encoder block for the class token only (the pooled token).  Against the same engine
+    with the full last block (EFFOCR_VIT_LAST_BLOCK_FULL=1, read at first use, hence two subprocesses) the embeddings
+    agree to fp16-operand noise, and both stay within the 1e-3 bound of the CPU oracle."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    script = (
+        "import sys, numpy as np, torch; sys.path.insert(0, '.');"
+        "from effocr_b200 import synth; from effocr_b200.pipeline import PackedCrops, RecognizerPipeline;"
+        "from oracle import vit as OV;"
+        "sd = OV.randomize_affine(OV.init_vit_state_dict('vit_small_patch16_224', seed=0));"
+        "pipe = RecognizerPipeline(sd, torch.zeros(1, 384), max_batch=64);"
+        "crops, _ = synth.synthetic_crops(40, seed=3);"
+        "px, im, bx, n = PackedCrops(crops).to_device();"
+        "np.save(sys.argv[1], pipe.embed_boxes(px, im, bx, n).cpu().numpy())")
+    outs = []
+    for full in ("0", "1"):
+        path = str(tmp_path / f"emb_{full}.npy")
+        env = dict(os.environ, EFFOCR_VIT_LAST_BLOCK_FULL=full)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, cwd=str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+        outs.append(np.load(path))
+    a, b = outs
+    rel = np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+    assert rel.max() < 1e-3, rel.max()
+    # and the oracle
+    import torch
+    from effocr_b200 import synth
+    from oracle import transform as OT, vit as OV
+    sd = OV.randomize_affine(OV.init_vit_state_dict("vit_small_patch16_224", seed=0))
+    crops, _ = synth.synthetic_crops(40, seed=3)
+    with torch.no_grad():
+        ref = OV.l2_normalize(OV.vit_forward(sd, torch.from_numpy(np.stack([OT.paired_transform(c) for c in crops])))).numpy()
+    for e in (a, b):
+        assert (np.linalg.norm(e - ref, axis=1) / np.linalg.norm(ref, axis=1)).max() <= 1e-3
