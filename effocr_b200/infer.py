@@ -221,7 +221,10 @@ def run_effocr(images_rgb, pipeline: EffOCRPipeline, batch_lines: int = 64, keys
     keys = list(range(len(images_rgb))) if keys is None else list(keys)
     out = {}
     starts = list(range(0, len(images_rgb), batch_lines))
-    for i0, res in zip(starts, pipeline.infer_batches((images_rgb[i:i + batch_lines] for i in starts), overlap=overlap)):
+    batches = (images_rgb[i:i + batch_lines] for i in starts)
+    # any object with infer_lines() works as a pipeline; the overlapped driver needs the two-stage interface
+    results = pipeline.infer_batches(batches, overlap=overlap) if hasattr(pipeline, "infer_batches") else map(pipeline.infer_lines, batches)
+    for i0, res in zip(starts, results):
         for k, r in zip(keys[i0:i0 + batch_lines], res):
             out[k] = r["text"]
     return out
