@@ -53,8 +53,7 @@ __device__ __forceinline__ void numpy_slice(int start, int stop, int n, int* lo,
 }
 
 constexpr int kCropMaxStage = 3072;  // staged source pixels (float4 each) per block: 48 KB
-constexpr int kCropHRows = 8;        // separable path: horizontally resampled band rows kept in shared memory (28 KB)
-constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4 + kCropHRows * 224 * 16;
+constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4;  // 53 KB: four blocks per SM
 
 template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16), 3 4x4-patch-major f16 ([n*3136, 48])
 __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restrict__ pixels,
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
   float4* s_src = reinterpret_cast<float4*>(crop_smem);                         // [kCropMaxStage]
   float4* s_xw = s_src + kCropMaxStage;                                         // [224] horizontal weights (<= 4 taps)
   int* s_xmn = reinterpret_cast<int*>(s_xw + OUT);                              // [224] first horizontal tap
-  float4* s_h = reinterpret_cast<float4*>(s_xmn + OUT);                         // [kCropHRows][224] horizontal pass
+  float4* s_h = nullptr;  // [nrows][224] horizontal pass: behind the staged band when both fit the 48 KB staging area
   bool fast = false;
   if (!empty) {
     const int S = h > w ? h : w;
@@ -125,7 +124,8 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
 #pragma unroll
       for (int yy = 0; yy < 4; ++yy) wys[yy] = yy < ty.sz ? tap_weight(ty, yy, invscale) : 0.f;
       const int oct = j0 >> 3;
-      if (nrows <= kCropHRows) {
+      if (nrows * (S + OUT) <= kCropMaxStage) {
+        s_h = s_src + nrows * S;
         // separable resampling, the order ATen itself uses (horizontal pass, then vertical): every band row is
         // resampled to the 224 output columns once (4 taps) and each output pixel then reads <= 4 of those values,
         // instead of 16 source pixels -- the same FMA sequence per pixel as the nested loop below (zero-weight taps
