@@ -256,7 +256,8 @@ def time_pipeline_c3(args, rec_pipe, rank, barrier):
     barrier()
     t0 = time.perf_counter()
     res = []
-    for batch_res in full.infer_batches(lines[i0:i0 + bl] for i0 in range(0, L, bl)):  # two-stage overlapped pipeline
+    overlap = os.environ.get("EFFOCR_PIPELINE_OVERLAP", "1") != "0"  # A/B switch for the two-stream software pipeline
+    for batch_res in full.infer_batches((lines[i0:i0 + bl] for i0 in range(0, L, bl)), overlap=overlap):
         res += batch_res
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
