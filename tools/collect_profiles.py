@@ -85,8 +85,8 @@ def traffic_of(rep):
 
 traffic = {}
 if (G / "layer_full.ncu-rep").exists():
-    # tools/profile_gemm.py launch order: qkv, attention, proj, layernorm, fused MLP block
-    order = ["gemm_qkv", "attention", "gemm_proj", "layernorm", "mlp_fused"]
+    # tools/profile_gemm.py launch order: qkv, attention, fused proj + residual + LN, layernorm, fused MLP block
+    order = ["gemm_qkv", "attention", "proj_ln", "layernorm", "mlp_fused"]
     for name, (_, t) in zip(order, traffic_of("layer_full.ncu-rep")):
         traffic[name] = t
 if (G / "misc_full.ncu-rep").exists():

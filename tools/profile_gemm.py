@@ -1,4 +1,4 @@
-"""ncu target: one ViT-S layer at batch 1024 (M = 201728): QKV GEMM, attention, proj GEMM, LayerNorm, fused MLP block;
+"""ncu target: one ViT-S layer at batch 1024 (M = 201728): QKV GEMM, attention, fused proj + residual + LayerNorm, LayerNorm, fused MLP block;
 one launch each after warm-up."""
 import sys
 import torch
@@ -19,12 +19,13 @@ b1152 = torch.randn(1152, device=dev); b384 = torch.randn(384, device=dev); b153
 qkv = torch.empty(M, 1152, device=dev, dtype=torch.float16)
 o1536 = torch.empty(M, 1536, device=dev, dtype=torch.float16)
 g = torch.ones(384, device=dev)
+h2 = torch.empty(M, 384, device=dev, dtype=torch.float16)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 for _ in range(reps):
     ops.gemm(h, wqkv, bias=b1152, out=qkv)
     ops.attention(qkv, 1024, 6)
-    ops.gemm(h, wproj, bias=b384, out_dtype=torch.float32, resid=x, out=x)
-    ops.layernorm(x, g, b384)
+    ops.proj_ln(x, h, wproj, b384, g, b384, out=h2)  # projection + residual + norm2 in one kernel
+    ops.layernorm(x, g, b384)                        # norm1 of the next block
     ops.mlp_fused(x, h, wfc1, b1536, wfc2, b384)  # fc1 + GELU + fc2 + residual in one kernel
 torch.cuda.synchronize()
 print("done")
