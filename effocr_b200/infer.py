@@ -120,7 +120,10 @@ class EffOCRPipeline:
     def stage_localize(self, images_rgb):
         """Stage 1 on the CURRENT stream: upload the u8 lines once, letterbox + YOLOv5s + NMS on the device, boxes to
         the host, reference box ordering / word ends / crop rectangles, rectangles back to the device."""
-        packed_images = ops.pack_images(images_rgb)  # ONE upload of the u8 lines for both GPU phases
+        pool = getattr(self, "_pin_pool", None)
+        if pool is None:
+            pool = self._pin_pool = ops.PinnedPool()
+        packed_images = ops.pack_images(images_rgb, pool=pool)  # ONE upload of the u8 lines for both GPU phases
         dets = self.localize(images_rgb, packed_images)
         per_line, all_rects = [], []
         for li, (im, det) in enumerate(zip(images_rgb, dets)):

@@ -168,8 +168,34 @@ def letterbox_resize(pixels: torch.Tensor, images: torch.Tensor, shapes, height:
     return out
 
 
-def pack_images(arrays, device="cuda", pinned: bool = True):
-    """Concatenate u8 HWC RGB images into one device buffer + descriptor table (one H2D copy each)."""
+class PinnedPool:
+    """A few reusable pinned staging buffers.  Allocating pinned memory per batch (cudaHostAlloc: an ioctl that page-locks
+    the range under a driver-wide lock) costs milliseconds and serialises ACROSS processes -- with several ranks per box the
+    per-batch allocations were the whole-pipeline scaling bottleneck.  A buffer is handed out again once the copy that
+    last read it has completed (CUDA event)."""
+
+    def __init__(self):
+        self._bufs = []  # [tensor, event or None]
+
+    def get(self, nbytes: int):
+        for ent in self._bufs:
+            if ent[0].numel() >= nbytes and (ent[1] is None or ent[1].query()):
+                ent[1] = None
+                return ent
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        ent = [t, None]
+        self._bufs.append(ent)
+        if len(self._bufs) > 8:  # unbounded growth guard: drop the oldest idle buffer
+            for i, e in enumerate(self._bufs):
+                if e is not ent and (e[1] is None or e[1].query()):
+                    del self._bufs[i]
+                    break
+        return ent
+
+
+def pack_images(arrays, device="cuda", pinned: bool = True, pool: PinnedPool | None = None):
+    """Concatenate u8 HWC RGB images into one device buffer + descriptor table (one H2D copy each).
+    `pool`: reuse pinned staging buffers across calls (see PinnedPool)."""
     descs = np.zeros(len(arrays), dtype=IMAGE_DESC_DTYPE)
     off = 0
     for i, a in enumerate(arrays):
@@ -177,13 +203,23 @@ def pack_images(arrays, device="cuda", pinned: bool = True):
         h, w, _ = a.shape
         descs[i] = (off, h, w, w * 3, 0)
         off += (h * w * 3 + 255) // 256 * 256
-    host = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
+    ent = None
+    if pool is not None and torch.cuda.is_available():
+        ent = pool.get(off + descs.nbytes + 256)
+        host = ent[0]
+    else:
+        host = torch.empty(max(off, 1) + descs.nbytes + 256, dtype=torch.uint8, pin_memory=pinned and torch.cuda.is_available())
     hv = host.numpy()
     for i, a in enumerate(arrays):
         o = int(descs[i]["offset"])
         hv[o:o + a.size] = np.ascontiguousarray(a).reshape(-1)
-    pixels = host.to(device, non_blocking=True)
-    images = torch.from_numpy(descs.view(np.uint8).copy()).to(device, non_blocking=True)
+    doff = (off + 255) // 256 * 256  # descriptors ride in the same pinned buffer: one upload for pixels + table
+    hv[doff:doff + descs.nbytes] = descs.view(np.uint8).reshape(-1)
+    dev = host[:doff + descs.nbytes].to(device, non_blocking=True)
+    if ent is not None:
+        ent[1] = torch.cuda.current_stream().record_event()
+    pixels = dev[:max(off, 1)]
+    images = dev[doff:doff + descs.nbytes]
     return pixels, images, descs
 
 
