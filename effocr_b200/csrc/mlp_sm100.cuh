@@ -313,7 +313,9 @@ mlp_fused_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_co
       // cycles), prefetching the residual rows into L2 (no change), residual add in registers with per-thread 64-byte
       // row slices (43 000 cycles: 32 cache lines per load / store instruction), residual add on the SM with the chunk
       // transposed through shared memory so that every global access is a full 128-byte row segment (~17 000 cycles:
-      // eight warps of dependent TMEM-load / transpose / load / store steps).
+      // eight warps of dependent TMEM-load / transpose / load / store steps), half of the columns through
+      // red.global.add.v4.f32 issued by the otherwise idle warps in parallel with the TMA reductions (no gain: the two
+      // paths share the per-SM reduction rate).
       constexpr int OCH = D / 2 / 32;  // 32-column chunks per draining warp
       const int m_row0 = tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       if (warp_idx == 4 && lane == 0) MLP_DBG(6 * 64 + 0);
