@@ -237,41 +237,36 @@ __global__ void __launch_bounds__(256) yolo_upsample2x_kernel(const __half* __re
 
 // SPPF: three chained 5x5 / stride 1 / pad 2 max-pools == window maxima of 5, 9, 13 (clipped at the border).
 // Reads channels [0, C) of the concat buffer, writes [C, 2C), [2C, 3C), [3C, 4C).
-__global__ void __launch_bounds__(256) yolo_sppf_pool_kernel(__half* __restrict__ buf, int ld, int B, int h, int w, int C) {
+__global__ void __launch_bounds__(256) yolo_pool5_kernel(__half* __restrict__ buf, int ld, int B, int h, int w, int C,
+                                                         int src_off, int dst_off) {
+  // one 5x5 / stride 1 / pad 2 max-pool of channels [src_off, src_off + C) into [dst_off, dst_off + C); SPPF chains three
+  // of them (windows 5, 9, 13) exactly as ultralytics defines it -- 75 loads per output instead of the 169 of a direct
+  // 13x13 window scan (the first version: 181 us per 64 lines)
   const int vpt = C / 8;
-  const long long total = static_cast<long long>(B) * h * w * vpt;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % vpt);
-    const long long pix = i / vpt;
+  const unsigned total = static_cast<unsigned>(B) * h * w * vpt;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned cv = i % vpt;
+    const unsigned pix = i / vpt;
     const int x = static_cast<int>(pix % w);
     const int y = static_cast<int>((pix / w) % h);
-    const int b = static_cast<int>(pix / (static_cast<long long>(w) * h));
+    const long long img = static_cast<long long>(pix / (static_cast<unsigned>(w) * h)) * h * w;
     const __half2 ninf = __float2half2_rn(-INFINITY);
-    __half2 m5[4], m9[4], m13[4];
+    __half2 m[4] = {ninf, ninf, ninf, ninf};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) m5[j] = m9[j] = m13[j] = ninf;
-    for (int dy = -6; dy <= 6; ++dy) {
+    for (int dy = -2; dy <= 2; ++dy) {
       const int yy = y + dy;
       if (yy < 0 || yy >= h) continue;
-      for (int dx = -6; dx <= 6; ++dx) {
+#pragma unroll
+      for (int dx = -2; dx <= 2; ++dx) {
         const int xx = x + dx;
         if (xx < 0 || xx >= w) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(buf + ((static_cast<long long>(b) * h + yy) * w + xx) * ld + cv * 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + (img + static_cast<long long>(yy) * w + xx) * ld + src_off + cv * 8);
         const __half2* hv = reinterpret_cast<const __half2*>(&v);
-        const int r = max(abs(dy), abs(dx));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          m13[j] = __hmax2(m13[j], hv[j]);
-          if (r <= 4) m9[j] = __hmax2(m9[j], hv[j]);
-          if (r <= 2) m5[j] = __hmax2(m5[j], hv[j]);
-        }
+        for (int j = 0; j < 4; ++j) m[j] = __hmax2(m[j], hv[j]);
       }
     }
-    __half* o = buf + pix * ld + cv * 8;
-    *reinterpret_cast<uint4*>(o + C) = *reinterpret_cast<const uint4*>(m5);
-    *reinterpret_cast<uint4*>(o + 2 * C) = *reinterpret_cast<const uint4*>(m9);
-    *reinterpret_cast<uint4*>(o + 3 * C) = *reinterpret_cast<const uint4*>(m13);
+    *reinterpret_cast<uint4*>(buf + static_cast<long long>(pix) * ld + dst_off + cv * 8) = *reinterpret_cast<const uint4*>(m);
   }
 }
 
@@ -567,7 +562,8 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
   r.conv1(x8, p5, YoloRun::slice(catS, 0));             // 9 SPPF cv1 -> first quarter of catS
   if (!r.status) {
     KernelScope ks(PROF_YOLO_MISC, s);
-    yolo_sppf_pool_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, 1024, B, H5, W5, 256);
+    for (int k = 0; k < 3; ++k)  // windows 5, 9, 13 = three chained 5x5 pools
+      yolo_pool5_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, 1024, B, H5, W5, 256, k * 256, (k + 1) * 256);
   }
   r.conv1(catS, p5, x9);                                // 9 SPPF cv2
   r.conv1(x9, p5, YoloRun::slice(cat22, 256));          // 10 -> second half of cat22

@@ -178,3 +178,21 @@ def test_edit_distance_and_cer():
     assert tp.edit_distance("kitten", "sitting") == 3 and tp.edit_distance("", "abc") == 3
     acc, cer = tp.textline_evaluation([("hello world", "hello world"), ("abc", "abd")])
     assert acc == 50.0 and abs(cer - 1 / 14) < 1e-12
+
+
+def test_pack_images_layout_and_pool_reuse():
+    """Host staging: pixels and the descriptor table travel in ONE buffer (descriptors 256-byte aligned behind the
+    pixels); a PinnedPool hands the same staging buffer out again once its copy has completed."""
+    from effocr_b200 import ops
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in [(64, 1024), (40, 333), (7, 5)]]
+    pool = ops.PinnedPool()
+    for _ in range(3):
+        pixels, images, descs = ops.pack_images(imgs, device="cpu", pool=pool)
+        table = np.frombuffer(images.numpy().tobytes(), dtype=ops.IMAGE_DESC_DTYPE)
+        assert np.array_equal(table, descs)
+        for im, d in zip(imgs, descs):
+            o = int(d["offset"])
+            assert o % 256 == 0 and (d["height"], d["width"], d["pitch"]) == (im.shape[0], im.shape[1], im.shape[1] * 3)
+            assert np.array_equal(pixels.numpy()[o:o + im.size].reshape(im.shape), im)
+    assert len(pool._bufs) <= 1 or not torch.cuda.is_available()
