@@ -709,9 +709,10 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 }
 
 // ------------------------------------------------------------------ one TMEM pass, two key blocks (default)
+template <bool kDbg>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
-                    __half* __restrict__ out, int batch, int H, float scale_log2e) {
+                    __half* __restrict__ out, int batch, int H, float scale_log2e, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
@@ -796,11 +797,22 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
       constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
       const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
+      // optional wait-time accounting (tools/att_timeline.py): cycles the issuing warp spends in each mbarrier wait
+      long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      auto twait = [&](uint64_t* bar, uint32_t par, int slot) {
+        if constexpr (kDbg) {
+          const long long t0 = clock64();
+          mbar_wait(bar, par);
+          acc[slot] += clock64() - t0;
+        } else {
+          mbar_wait(bar, par);
+        }
+      };
       auto issue_s = [&](int g, int it) {
         const uint32_t par = it & 1;
         const int s = it & 1;
-        mbar_wait(&q_full[g], par);
-        mbar_wait(&t_free[g], par ^ 1);  // region g (S / O1 / O2 columns) drained by the previous pair's epilogue
+        twait(&q_full[g], par, 1 + 4 * g);
+        twait(&t_free[g], par ^ 1, 2 + 4 * g);  // region g (S / O1 / O2 columns) drained by the previous pair's epilogue
         tcgen05_fence_after();
         const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
         const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
@@ -816,7 +828,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       auto issue_pv = [&](int g, int it) {
         const uint32_t par = it & 1;
         const uint32_t pbase = p_base + g * kAtPBytes;
-        mbar_wait(&p_full[g], par);  // key block A of P written, S columns 0..127 consumed by all four warps
+        twait(&p_full[g], par, 3 + 4 * g);  // key block A of P written, S columns 0..127 consumed by all four warps
         tcgen05_fence_after();
         if (leader_lane) {
 #pragma unroll
@@ -827,7 +839,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
         }
         __syncwarp();
-        mbar_wait(&pb_full[g], par);  // key block B written, all of S consumed
+        twait(&pb_full[g], par, 4 + 4 * g);  // key block B written, all of S consumed
         tcgen05_fence_after();
         if (leader_lane) {
 #pragma unroll
@@ -847,9 +859,10 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         __syncwarp();
       };
       int it = 0;
+      const long long t_begin = kDbg ? clock64() : 0;
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
         const int s = it & 1;
-        mbar_wait(&k_full[s], (it >> 1) & 1);
+        twait(&k_full[s], (it >> 1) & 1, 0);
         issue_s(0, it);
         if (it > 0) {
           issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
@@ -857,12 +870,17 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         }
         issue_s(1, it);
         commit(&k_empty[s]);
-        mbar_wait(v_full, it & 1);  // V(it), reloaded after PV1(it-1) retired
+        twait(v_full, it & 1, 9);  // V(it), reloaded after PV1(it-1) retired
         issue_pv(0, it);
       }
       if (it > 0) {
         issue_pv(1, it - 1);
         commit(v_empty);
+      }
+      if (kDbg && blockIdx.x == 0 && leader_lane) {
+        for (int i = 0; i < 10; ++i) dbg[i] = acc[i];
+        dbg[10] = clock64() - t_begin;
+        dbg[11] = it;
       }
     }
   } else if (warp_idx >= 4) {
@@ -878,10 +896,13 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
     uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
     int it = 0;
+    long long a_s = 0, a_c = 0, a_o = 0, a_e = 0;  // dbg: cycles in the s_full wait / softmax / o_full wait / epilogue
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
       const int b = bh / H, h = bh % H;
       const uint32_t par = it & 1;
+      const long long ts0 = kDbg ? clock64() : 0;
       mbar_wait(&s_full[g], par);
+      const long long ts1 = kDbg ? clock64() : 0;
       tcgen05_fence_after();
       float mA = 0.f, mB = 0.f, lA = 1.f, lB = 1.f;
       // rows 224..255 (group 1, lane quarter 3) do not exist (197 tokens): that warp only keeps the hand-shakes going;
@@ -971,7 +992,9 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       const float aA = ex2_approx((mA - m) * scale_log2e), aB = ex2_approx((mB - m) * scale_log2e);
       const float inv = 1.0f / fmaf(lA, aA, lB * aB);
       const float wA = aA * inv, wB = aB * inv;
+      const long long ts2 = kDbg ? clock64() : 0;
       mbar_wait(&o_full[g], par);
+      const long long ts3 = kDbg ? clock64() : 0;
       tcgen05_fence_after();
       const int tok = g * 128 + r;
       __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64;
@@ -1001,6 +1024,379 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           }
         }
       }
+      if constexpr (kDbg) {
+        a_s += ts1 - ts0; a_c += ts2 - ts1; a_o += ts3 - ts2; a_e += clock64() - ts3;
+      }
+    }
+    if (kDbg && blockIdx.x == 0 && q == 0 && lane == 0) {
+      dbg[12 + 4 * g] = a_s; dbg[13 + 4 * g] = a_c; dbg[14 + 4 * g] = a_o; dbg[15 + 4 * g] = a_e;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ one TMEM pass, three key blocks, 16 softmax warps
+// The two-block kernel above is bound by its softmax warps: tools/att_timeline.py shows each of them busy ~5 700 of the
+// 7 300 cycles a (image, head) unit takes (3 900 softmax + 1 800 epilogue), one exponential every 8 cycles per warp being
+// the MUFU rate a single warp can draw.  Here every query row is served by TWO threads in different warps: warp X takes
+// keys 0..63 and then 64..127, warp Y keys 128..196, each key block with its own maximum and its own P.V accumulator
+// (O1 | O2 | O3 alias the S columns of their own key block, so the TMEM budget is unchanged); the epilogue is split by
+// output columns (X: 0..31, Y: 32..63) after the two threads exchanged (max, sum) per block through shared memory.
+// 64 live scores per thread instead of 128 keeps the 640-thread CTA inside 102 registers.
+constexpr int kAt3Threads = 128 + 16 * 32;
+constexpr int kAt3StatBytes = 8192;  // [2 groups][6 values: m1 l1 m2 l2 m3 l3][128 rows] fp32 (6 KB used)
+constexpr int kAt3SmemBytes = kAtSmemBytes + kAt3StatBytes;
+
+template <bool kDbg>
+__global__ void __launch_bounds__(kAt3Threads, 1)
+attention_tc3b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                      __half* __restrict__ out, int batch, int H, float scale_log2e, long long* dbg) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
+  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // [2 unit parities] x 26 KB
+  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 26 KB
+  uint8_t* smem_p = smem_v + kAtKVBytes;               // [2 groups] x 52 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
+  uint64_t* q_full = bars;         // [2]
+  uint64_t* q_empty = bars + 2;    // [2]
+  uint64_t* k_full = bars + 4;     // [2]
+  uint64_t* k_empty = bars + 6;    // [2]
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_empty = bars + 9;
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p1_full = bars + 12;   // [2] keys 0..63 of P written
+  uint64_t* p2_full = bars + 14;   // [2] keys 64..127
+  uint64_t* p3_full = bars + 16;   // [2] keys 128..207
+  uint64_t* o_full = bars + 18;    // [2]
+  uint64_t* t_free = bars + 20;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* stats = reinterpret_cast<float*>(smem_p + 2 * kAtPBytes + 256);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int D = H * 64;
+  const int num_bh = batch * H;
+
+  if (warp_idx == 0 && elect_one_sync()) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+  }
+  if (warp_idx == 1 && elect_one_sync()) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p1_full[i], 4);
+      mbar_init(&p2_full[i], 4);
+      mbar_init(&p3_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&t_free[i], 8);
+    }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp_idx == 0) {
+    // ---------------- TMA producer (same schedule as the two-block kernel)
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+        const int b = bh / H, h = bh % H;
+        const int row0 = b * kAtT;
+        const int s = it & 1;
+        const uint32_t par = it & 1, par2 = (it >> 1) & 1;
+        mbar_wait(&k_empty[s], par2 ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], kAtKVBytes);
+        tma_load_2d(&tma_kv, &k_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&q_empty[g], par ^ 1);
+          mbar_arrive_expect_tx(&q_full[g], kAtQBytes);
+          tma_load_2d(&tma_q, &q_full[g], smem_q + g * kAtQBytes, h * 64, row0 + g * 128);
+        }
+        mbar_wait(v_empty, par ^ 1);
+        mbar_arrive_expect_tx(v_full, kAtKVBytes);
+        tma_load_2d(&tma_kv, v_full, smem_v, 2 * D + h * 64, row0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ---------------- MMA issuer (warp-uniform loop).  Issue order per unit i:  S0(i), PV1(i-1), S1(i), PV0(i).
+    const bool leader_lane = elect_one_sync();
+    constexpr uint32_t idesc_s = make_idesc_f16(128, kAtN);
+    constexpr uint32_t idesc_o = make_idesc_f16_bmn(128, 64);
+    const uint32_t q_base = smem_u32(smem_q), k_base = smem_u32(smem_k), v_base = smem_u32(smem_v), p_base = smem_u32(smem_p);
+    long long acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto twait = [&](uint64_t* bar, uint32_t par, int slot) {
+      if constexpr (kDbg) {
+        const long long t0 = clock64();
+        mbar_wait(bar, par);
+        acc[slot] += clock64() - t0;
+      } else {
+        mbar_wait(bar, par);
+      }
+    };
+    auto issue_s = [&](int g, int it) {
+      const uint32_t par = it & 1;
+      const int s = it & 1;
+      twait(&q_full[g], par, 1 + 4 * g);
+      twait(&t_free[g], par ^ 1, 2 + 4 * g);  // region g (S / O1 / O2 / O3 columns) drained by the previous unit's epilogue
+      tcgen05_fence_after();
+      const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
+      const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
+      if (leader_lane) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
+        umma_commit(&q_empty[g]);
+        umma_commit(&s_full[g]);
+      }
+      __syncwarp();
+    };
+    // O1 (columns 0..63 of the region) = P[:, 0:64] V[0:64], O2 (64..127) = P[:, 64:128] V[64:128],
+    // O3 (128..191) = P[:, 128:208] V[128:208]; each waits only for its own key block of P
+    auto issue_pv = [&](int g, int it) {
+      const uint32_t par = it & 1;
+      const uint32_t pbase = p_base + g * kAtPBytes;
+      const uint32_t tO = tmem_base + g * kAtTmemRegion;
+      twait(&p1_full[g], par, 3 + 4 * g);
+      tcgen05_fence_after();
+      if (leader_lane) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tO, make_sw128_kmajor_desc(pbase) + 2 * ks, make_sw128_mnmajor_desc(v_base + ks * 2048), idesc_o, ks ? 1u : 0u);
+      }
+      __syncwarp();
+      twait(&p3_full[g], par, 4 + 4 * g);
+      tcgen05_fence_after();
+      if (leader_lane) {
+#pragma unroll
+        for (int ks = 8; ks < 12; ++ks)
+          umma_f16(tO + 128, make_sw128_kmajor_desc(pbase + 2 * kAtQBytes) + 2 * (ks & 3), make_sw128_mnmajor_desc(v_base + ks * 2048),
+                   idesc_o, ks > 8 ? 1u : 0u);
+        umma_f16(tO + 128, make_sw32_kmajor_desc(pbase + kAtPMain), make_sw128_mnmajor_desc(v_base + 12 * 2048), idesc_o, 1u);
+      }
+      __syncwarp();
+      twait(&p2_full[g], par, 4 + 4 * g);
+      tcgen05_fence_after();
+      if (leader_lane) {
+#pragma unroll
+        for (int ks = 4; ks < 8; ++ks)
+          umma_f16(tO + 64, make_sw128_kmajor_desc(pbase + kAtQBytes) + 2 * (ks & 3), make_sw128_mnmajor_desc(v_base + ks * 2048),
+                   idesc_o, ks > 4 ? 1u : 0u);
+        umma_commit(&o_full[g]);
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (leader_lane) umma_commit(bar);
+      __syncwarp();
+    };
+    int it = 0;
+    const long long t_begin = kDbg ? clock64() : 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+      const int s = it & 1;
+      twait(&k_full[s], (it >> 1) & 1, 0);
+      issue_s(0, it);
+      if (it > 0) {
+        issue_pv(1, it - 1);  // V(it-1) is still resident: its buffer is released right here
+        commit(v_empty);
+      }
+      issue_s(1, it);
+      commit(&k_empty[s]);
+      twait(v_full, it & 1, 9);  // V(it), reloaded after PV1(it-1) retired
+      issue_pv(0, it);
+    }
+    if (it > 0) {
+      issue_pv(1, it - 1);
+      commit(v_empty);
+    }
+    if (kDbg && blockIdx.x == 0 && leader_lane) {
+      for (int i = 0; i < 10; ++i) dbg[i] = acc[i];
+      dbg[10] = clock64() - t_begin;
+      dbg[11] = it;
+    }
+  } else if (warp_idx >= 4) {
+    // ---------------- softmax + epilogue: group g = query tile, (warp X, warp Y) = the two threads of a query row
+    const int idx = warp_idx - 4;
+    const int g = idx >> 3;
+    const int half = (idx >> 2) & 1;  // 0: warp X (keys 0..127, output columns 0..31), 1: warp Y (keys 128..196, columns 32..63)
+    const int q = idx & 3;            // == warp_idx & 3: the TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;      // row inside the 128-row tile
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
+    uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
+    uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    float* st = stats + g * 6 * 128 + r;  // value s of this row at st[s * 128]
+    const int pair_bar = 1 + g * 4 + q;
+    // rows 224..255 (group 1, lane quarter 3) do not exist (197 tokens): those warps only keep the hand-shakes going
+    const bool live = !(g == 1 && q == 3);
+    long long a_s = 0, a_c = 0, a_o = 0, a_e = 0;  // dbg: cycles in the s_full wait / softmax / o_full wait / epilogue
+    // one 64-key block: scores from TMEM columns tcol.., P to the SWIZZLE_128B chunk, returns (max, sum)
+    auto block64 = [&](uint32_t tcol, uint8_t* chunk, float& m_out, float& l_out) {
+      uint32_t v[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(trow + tcol + c * 16, v[c]);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
+      const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      const float moff = m * scale_log2e;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 pk[2];
+        __half2* ph = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff));
+          s4[(2 * t) & 3] += p0;
+          s4[(2 * t + 1) & 3] += p1;
+          ph[t] = __floats2half2_rn(p0, p1);
+        }
+        *reinterpret_cast<uint4*>(chunk + (((2 * c) ^ (r & 7)) << 4)) = pk[0];
+        *reinterpret_cast<uint4*>(chunk + (((2 * c + 1) ^ (r & 7)) << 4)) = pk[1];
+      }
+      m_out = m;
+      l_out = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    };
+    auto publish = [&](uint64_t* bar) {  // P block written: visible to the MMA (async proxy), then signal
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    int it = 0;
+    for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
+      const int b = bh / H, h = bh % H;
+      const uint32_t par = it & 1;
+      const long long ts0 = kDbg ? clock64() : 0;
+      mbar_wait(&s_full[g], par);
+      const long long ts1 = kDbg ? clock64() : 0;
+      tcgen05_fence_after();
+      if (half == 0) {
+        float m1 = 0.f, l1 = 1.f, m2 = 0.f, l2 = 1.f;
+        if (live) block64(0, pmain, m1, l1);
+        publish(&p1_full[g]);
+        if (live) block64(64, pmain + kAtQBytes, m2, l2);
+        publish(&p2_full[g]);
+        st[0] = m1; st[128] = l1; st[256] = m2; st[384] = l2;
+      } else {
+        float m3 = 0.f, l3 = 1.f;
+        if (live) {  // keys 128..191 as a full block, then the five valid keys 192..196 of the SWIZZLE_32B tail
+          uint32_t v[4][16], tl[8];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x16(trow + 128 + c * 16, v[c]);
+          tmem_ld_32x32b_x8(trow + 192, tl);
+          tmem_ld_wait();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
+#pragma unroll
+          for (int e = 0; e < 5; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(tl[e]));
+          m3 = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          const float moff = m3 * scale_log2e;
+          float s4[4] = {0.f, 0.f, 0.f, 0.f};
+          uint8_t* chunk = pmain + 2 * kAtQBytes;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint4 pk[2];
+            __half2* ph = reinterpret_cast<__half2*>(pk);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff));
+              s4[(2 * t) & 3] += p0;
+              s4[(2 * t + 1) & 3] += p1;
+              ph[t] = __floats2half2_rn(p0, p1);
+            }
+            *reinterpret_cast<uint4*>(chunk + (((2 * c) ^ (r & 7)) << 4)) = pk[0];
+            *reinterpret_cast<uint4*>(chunk + (((2 * c + 1) ^ (r & 7)) << 4)) = pk[1];
+          }
+          {
+            float pt[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              pt[e] = e < 5 ? ex2_approx(fmaf(__uint_as_float(tl[e]), scale_log2e, -moff)) : 0.f;  // keys >= 197 masked
+              s4[e & 3] += pt[e];
+            }
+            uint4 pk0;
+            __half2* ph = reinterpret_cast<__half2*>(&pk0);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(pt[2 * t], pt[2 * t + 1]);
+            *reinterpret_cast<uint4*>(ptail + ((0 ^ ((r >> 2) & 1)) << 4)) = pk0;  // SWIZZLE_32B: bit 4 ^= bit 7
+            *reinterpret_cast<uint4*>(ptail + ((1 ^ ((r >> 2) & 1)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+          l3 = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        }
+        publish(&p3_full[g]);
+        st[512] = m3; st[640] = l3;
+      }
+      named_bar_sync_at(pair_bar, 64);  // both threads of the row have published their (max, sum) pairs
+      // ---- epilogue: (O1 a1 + O2 a2 + O3 a3) / (l1 a1 + l2 a2 + l3 a3) -> fp16 -> global, 32 output columns per thread
+      const float m1 = st[0], l1 = st[128], m2 = st[256], l2 = st[384], m3 = st[512], l3 = st[640];
+      const float m = fmaxf(fmaxf(m1, m2), m3);
+      const float a1 = ex2_approx((m1 - m) * scale_log2e), a2 = ex2_approx((m2 - m) * scale_log2e),
+                  a3 = ex2_approx((m3 - m) * scale_log2e);
+      const float inv = 1.0f / fmaf(l1, a1, fmaf(l2, a2, l3 * a3));
+      const float w1 = a1 * inv, w2 = a2 * inv, w3 = a3 * inv;
+      const long long ts2 = kDbg ? clock64() : 0;
+      mbar_wait(&o_full[g], par);
+      const long long ts3 = kDbg ? clock64() : 0;
+      tcgen05_fence_after();
+      const int tok = g * 128 + r;
+      __half* dst = out + (static_cast<long long>(b) * kAtT + tok) * D + h * 64 + half * 32;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o1[16], o2[16], o3[16];
+        tmem_ld_32x32b_x16(trow + half * 32 + hh * 16, o1);
+        tmem_ld_32x32b_x16(trow + 64 + half * 32 + hh * 16, o2);
+        tmem_ld_32x32b_x16(trow + 128 + half * 32 + hh * 16, o3);
+        tmem_ld_wait();
+        if (hh == 1) {  // my part of O is read: region g is free for the next unit's S once all eight warps arrive
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_free[g]);
+        }
+        if (tok < kAtT) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int e = 8 * j + 2 * t;
+              ph[t] = __floats2half2_rn(
+                  fmaf(__uint_as_float(o1[e]), w1, fmaf(__uint_as_float(o2[e]), w2, __uint_as_float(o3[e]) * w3)),
+                  fmaf(__uint_as_float(o1[e + 1]), w1, fmaf(__uint_as_float(o2[e + 1]), w2, __uint_as_float(o3[e + 1]) * w3)));
+            }
+            *reinterpret_cast<uint4*>(dst + hh * 16 + 8 * j) = pk;
+          }
+        }
+      }
+      if constexpr (kDbg) {
+        a_s += ts1 - ts0; a_c += ts2 - ts1; a_o += ts3 - ts2; a_e += clock64() - ts3;
+      }
+    }
+    if (kDbg && blockIdx.x == 0 && q == 0 && lane == 0) {
+      const int o = 12 + 4 * g + 8 * half;
+      dbg[o] = a_s; dbg[o + 1] = a_c; dbg[o + 2] = a_o; dbg[o + 3] = a_e;
     }
   }
   tcgen05_fence_before();

@@ -87,7 +87,7 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
 }
 
 // impl 0: tcgen05 kernel, one TMEM pass over S with two key blocks combined flash-attention style (default); A/B
-// variants via EFFOCR_ATTENTION_SOFTMAX or impl: 2 = two TMEM passes, 3 (env 1) = single pass via fp16 deltas in the P
+// variants via EFFOCR_ATTENTION_SOFTMAX or impl: 5 = three key blocks / 16 softmax warps, 2 = two TMEM passes, 3 (env 1) = single pass via fp16 deltas in the P
 // tile, 4 = two passes with 16 softmax warps; impl 1: first-generation mma.sync kernel
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
@@ -106,7 +106,10 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt16SmemBytes));
-      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
       attr = true;
     }
     static const int env_variant = [] {
@@ -117,7 +120,8 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     if (impl == 2) variant = 2;
     else if (impl == 3) variant = 1;
     else if (impl == 4) variant = 4;
-    else if (env_variant == 1 || env_variant == 2 || env_variant == 4) variant = env_variant;
+    else if (impl == 5) variant = 5;
+    else if (env_variant == 1 || env_variant == 2 || env_variant == 4 || env_variant == 5) variant = env_variant;
     const long long rows = static_cast<long long>(batch) * T;
     const int D = H * 64;
     CUtensorMap tq, tkv;
@@ -129,7 +133,17 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     if (variant == 1) attention_tc_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
     else if (variant == 2) attention_tc_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
     else if (variant == 4) attention_tc16_kernel<<<grid, kAt16Threads, kAt16SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
-    else attention_tc2b_kernel<<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
+    else if (variant == 5) {
+      const char* e = getenv("EFFOCR_ATT_DBG_PTR");
+      long long* dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+      if (dbg) attention_tc3b_kernel<true><<<grid, kAt3Threads, kAt3SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, dbg);
+      else attention_tc3b_kernel<false><<<grid, kAt3Threads, kAt3SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, nullptr);
+    } else {
+      const char* e = getenv("EFFOCR_ATT_DBG_PTR");  // tools/att_timeline.py: device buffer of 32 int64 receiving wait-time totals
+      long long* dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+      if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, dbg);
+      else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, nullptr);
+    }
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

@@ -86,7 +86,7 @@ def test_layernorm(dim, f32):
     assert _rel(out, ref) < (2e-6 if f32 else 4e-4)
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("batch,heads", [(1, 3), (5, 6), (64, 6), (200, 3)])
 def test_attention(batch, heads, impl):
     from effocr_b200 import ops
