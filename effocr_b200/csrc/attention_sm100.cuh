@@ -709,23 +709,44 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 }
 
 // ------------------------------------------------------------------ one TMEM pass, two key blocks (default)
-template <bool kDbg>
+// Output tile through TMA (kTmaOut): each softmax warp stages its 32 rows x 64 fp16 in the (dead) first P chunk of its group,
+// SWIZZLE_128B, and one lane issues a 4-D tensor store {64 columns, 32 tokens, 1 image} -- tokens >= 197 are clipped by the
+// tensor map.  The per-thread row stores it replaces (eight 16-byte pieces 768 B apart per warp instruction) cost 20 % of the
+// kernel (tools/att_ablate.py: 160 -> 129 us without them).
+__device__ __forceinline__ void at_tma_store_4d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                                int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void at_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void at_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void at_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// kAblate (timing experiments only, results are wrong): 1 = no global stores, 2 = no P stores to shared memory,
+// 4 = exponentials replaced by an FMA (no MUFU), 8 = no maximum search
+template <bool kDbg, int kAblate = 0, bool kTmaOut = true>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
+                      const __grid_constant__ CUtensorMap tma_o,
                     __half* __restrict__ out, int batch, int H, float scale_log2e, long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
-  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // [2 pair parities] x 26 KB
-  uint8_t* smem_v = smem_k + 2 * kAtKVBytes;           // 26 KB
-  uint8_t* smem_p = smem_v + kAtKVBytes;               // [2 groups] x 52 KB
+  // K single-buffered, V double-buffered: K(i+1) is fetched between S1(i) and S0(i+1), half a unit apart, while V(i) stays
+  // live until P.V of group 1 retires in the NEXT iteration -- with one V buffer the issuing warp waited 1 700 cycles per
+  // unit for V (tools/att_timeline.py)
+  uint8_t* smem_k = smem_q + 2 * kAtQBytes;            // 26 KB
+  uint8_t* smem_v = smem_k + kAtKVBytes;               // [2 unit parities] x 26 KB
+  uint8_t* smem_p = smem_v + 2 * kAtKVBytes;           // [2 groups] x 52 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_p + 2 * kAtPBytes);
   uint64_t* q_full = bars;         // [2]
   uint64_t* q_empty = bars + 2;    // [2]
-  uint64_t* k_full = bars + 4;     // [2]
-  uint64_t* k_empty = bars + 6;    // [2]
-  uint64_t* v_full = bars + 8;
-  uint64_t* v_empty = bars + 9;
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_empty = bars + 5;
+  uint64_t* v_full = bars + 6;     // [2]
+  uint64_t* v_empty = bars + 8;    // [2]
   uint64_t* s_full = bars + 10;    // [2]
   uint64_t* p_full = bars + 12;    // [2]
   uint64_t* o_full = bars + 14;    // [2]
@@ -741,21 +762,22 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   if (warp_idx == 0 && elect_one_sync()) {
     tma_prefetch_desc(&tma_q);
     tma_prefetch_desc(&tma_kv);
+    if (kTmaOut) tma_prefetch_desc(&tma_o);
   }
   if (warp_idx == 1 && elect_one_sync()) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);
       mbar_init(&pb_full[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&t_free[i], 4);
     }
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
     fence_barrier_init();
   }
   if (warp_idx == 2) {
@@ -776,17 +798,17 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         const int row0 = b * kAtT;
         const int s = it & 1;
         const uint32_t par = it & 1, par2 = (it >> 1) & 1;
-        mbar_wait(&k_empty[s], par2 ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], kAtKVBytes);
-        tma_load_2d(&tma_kv, &k_full[s], smem_k + s * kAtKVBytes, D + h * 64, row0);
+        mbar_wait(k_empty, par ^ 1);
+        mbar_arrive_expect_tx(k_full, kAtKVBytes);
+        tma_load_2d(&tma_kv, k_full, smem_k, D + h * 64, row0);
         for (int g = 0; g < 2; ++g) {
           mbar_wait(&q_empty[g], par ^ 1);
           mbar_arrive_expect_tx(&q_full[g], kAtQBytes);
           tma_load_2d(&tma_q, &q_full[g], smem_q + g * kAtQBytes, h * 64, row0 + g * 128);
         }
-        mbar_wait(v_empty, par ^ 1);
-        mbar_arrive_expect_tx(v_full, kAtKVBytes);
-        tma_load_2d(&tma_kv, v_full, smem_v, 2 * D + h * 64, row0);
+        mbar_wait(&v_empty[s], par2 ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], kAtKVBytes);
+        tma_load_2d(&tma_kv, &v_full[s], smem_v + s * kAtKVBytes, 2 * D + h * 64, row0);
       }
     }
   } else if (warp_idx == 1) {
@@ -810,12 +832,11 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       };
       auto issue_s = [&](int g, int it) {
         const uint32_t par = it & 1;
-        const int s = it & 1;
         twait(&q_full[g], par, 1 + 4 * g);
         twait(&t_free[g], par ^ 1, 2 + 4 * g);  // region g (S / O1 / O2 columns) drained by the previous pair's epilogue
         tcgen05_fence_after();
         const uint64_t dq = make_sw128_kmajor_desc(q_base + g * kAtQBytes);
-        const uint64_t dk = make_sw128_kmajor_desc(k_base + s * kAtKVBytes);
+        const uint64_t dk = make_sw128_kmajor_desc(k_base);
         if (leader_lane) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(tmem_base + g * kAtTmemRegion, dq + 2 * k, dk + 2 * k, idesc_s, k ? 1u : 0u);
@@ -828,13 +849,14 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       auto issue_pv = [&](int g, int it) {
         const uint32_t par = it & 1;
         const uint32_t pbase = p_base + g * kAtPBytes;
+        const uint32_t vb = v_base + (it & 1) * kAtKVBytes;  // V of this unit
         twait(&p_full[g], par, 3 + 4 * g);  // key block A of P written, S columns 0..127 consumed by all four warps
         tcgen05_fence_after();
         if (leader_lane) {
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
-            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            const uint64_t dv = make_sw128_mnmajor_desc(vb + ks * 2048);
             umma_f16(tmem_base + g * kAtTmemRegion, dp, dv, idesc_o, ks ? 1u : 0u);
           }
         }
@@ -845,11 +867,11 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
           for (int ks = 8; ks < 12; ++ks) {
             const uint64_t dp = make_sw128_kmajor_desc(pbase + (ks >> 2) * kAtQBytes) + 2 * (ks & 3);
-            const uint64_t dv = make_sw128_mnmajor_desc(v_base + ks * 2048);
+            const uint64_t dv = make_sw128_mnmajor_desc(vb + ks * 2048);
             umma_f16(tmem_base + g * kAtTmemRegion + 64, dp, dv, idesc_o, ks > 8 ? 1u : 0u);
           }
           umma_f16(tmem_base + g * kAtTmemRegion + 64, make_sw32_kmajor_desc(pbase + kAtPMain),
-                   make_sw128_mnmajor_desc(v_base + 12 * 2048), idesc_o, 1u);
+                   make_sw128_mnmajor_desc(vb + 12 * 2048), idesc_o, 1u);
           umma_commit(&o_full[g]);
         }
         __syncwarp();
@@ -861,21 +883,20 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       int it = 0;
       const long long t_begin = kDbg ? clock64() : 0;
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
-        const int s = it & 1;
-        twait(&k_full[s], (it >> 1) & 1, 0);
+        twait(k_full, it & 1, 0);
         issue_s(0, it);
         if (it > 0) {
-          issue_pv(1, it - 1);   // V(it-1) is still resident: its buffer is released right here
-          commit(v_empty);
+          issue_pv(1, it - 1);   // V(it-1) lives in the other V buffer, released right here
+          commit(&v_empty[(it - 1) & 1]);
         }
         issue_s(1, it);
-        commit(&k_empty[s]);
-        twait(v_full, it & 1, 9);  // V(it), reloaded after PV1(it-1) retired
+        commit(k_empty);         // K(it+1) may land now; it is needed at S0(it+1)
+        twait(&v_full[it & 1], (it >> 1) & 1, 9);
         issue_pv(0, it);
       }
       if (it > 0) {
         issue_pv(1, it - 1);
-        commit(v_empty);
+        commit(&v_empty[(it - 1) & 1]);
       }
       if (kDbg && blockIdx.x == 0 && leader_lane) {
         for (int i = 0; i < 10; ++i) dbg[i] = acc[i];
@@ -895,6 +916,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
     uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
     uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    auto ex2x = [&](float x) { return (kAblate & 4) ? fmaf(x, 0.001f, 0.5f) : ex2_approx(x); };
     int it = 0;
     long long a_s = 0, a_c = 0, a_o = 0, a_e = 0;  // dbg: cycles in the s_full wait / softmax / o_full wait / epilogue
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
@@ -904,6 +926,10 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
       mbar_wait(&s_full[g], par);
       const long long ts1 = kDbg ? clock64() : 0;
       tcgen05_fence_after();
+      if (kTmaOut) {  // the previous unit's output tile has left the first P chunk
+        if (lane == 0) at_store_wait_read0();
+        __syncwarp();
+      }
       float mA = 0.f, mB = 0.f, lA = 1.f, lB = 1.f;
       // rows 224..255 (group 1, lane quarter 3) do not exist (197 tokens): that warp only keeps the hand-shakes going;
       // whatever its P rows hold feeds only output rows that are never stored
@@ -918,7 +944,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
         for (int c = 0; c < 8; ++c)
 #pragma unroll
           for (int e = 0; e < 16; ++e) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
-        mA = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        mA = (kAblate & 8) ? __uint_as_float(v[0][0]) : fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float moff = mA * scale_log2e;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -927,16 +953,20 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           __half2* ph = reinterpret_cast<__half2*>(pk);
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff));
+            const float p0 = ex2x(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff));
+            const float p1 = ex2x(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff));
             s4[(2 * t) & 3] += p0;
             s4[(2 * t + 1) & 3] += p1;
             ph[t] = __floats2half2_rn(p0, p1);
           }
           uint8_t* chunk = pmain + (c >> 2) * kAtQBytes;
           const int piece = (c & 3) * 2;
-          *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
-          *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+          if (!(kAblate & 2)) {
+            *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
+            *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+          } else if (pk[0].x == 0x12345u) {
+            *reinterpret_cast<uint4*>(chunk) = pk[1];
+          }
         }
         lA = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       }
@@ -955,7 +985,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
           for (int e = 0; e < 16; ++e)
             if (c < 4 || e < 5) m4[e & 3] = fmaxf(m4[e & 3], __uint_as_float(v[c][e]));
-        mB = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        mB = (kAblate & 8) ? __uint_as_float(v[0][0]) : fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float moff = mB * scale_log2e;
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -965,13 +995,15 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
 #pragma unroll
           for (int t = 0; t < 8; ++t) {
             const bool ok0 = c < 4 || 2 * t < 5, ok1 = c < 4 || 2 * t + 1 < 5;  // keys >= 197 masked
-            const float p0 = ok0 ? ex2_approx(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff)) : 0.f;
-            const float p1 = ok1 ? ex2_approx(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff)) : 0.f;
+            const float p0 = ok0 ? ex2x(fmaf(__uint_as_float(v[c][2 * t]), scale_log2e, -moff)) : 0.f;
+            const float p1 = ok1 ? ex2x(fmaf(__uint_as_float(v[c][2 * t + 1]), scale_log2e, -moff)) : 0.f;
             s4[(2 * t) & 3] += p0;
             s4[(2 * t + 1) & 3] += p1;
             ph[t] = __floats2half2_rn(p0, p1);
           }
-          if (c < 4) {
+          if (kAblate & 2) {
+            if (pk[0].x == 0x12345u) *reinterpret_cast<uint4*>(pmain) = pk[1];
+          } else if (c < 4) {
             uint8_t* chunk = pmain + 2 * kAtQBytes;
             const int piece = c * 2;
             *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
@@ -1009,7 +1041,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_free[g]);
         }
-        if (tok < kAtT) {
+        if (kTmaOut || tok < kAtT) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 pk;
@@ -1020,14 +1052,24 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
               ph[t] = __floats2half2_rn(fmaf(__uint_as_float(o1[e]), wA, __uint_as_float(o2[e]) * wB),
                                         fmaf(__uint_as_float(o1[e + 1]), wA, __uint_as_float(o2[e + 1]) * wB));
             }
-            *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * j) = pk;
+            if (kTmaOut) *reinterpret_cast<uint4*>(pmain + (((hh * 4 + j) ^ (r & 7)) << 4)) = pk;
+            else if (!(kAblate & 1) || pk.x == 0x12345u) *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * j) = pk;
           }
+        }
+      }
+      if (kTmaOut) {
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && live) {
+          at_tma_store_4d(&tma_o, smem_p + g * kAtPBytes + q * 32 * 128, h * 64, g * 128 + q * 32, b, 0);
+          at_store_commit();
         }
       }
       if constexpr (kDbg) {
         a_s += ts1 - ts0; a_c += ts2 - ts1; a_o += ts3 - ts2; a_e += clock64() - ts3;
       }
     }
+    if (kTmaOut && lane == 0) at_store_wait_all0();
     if (kDbg && blockIdx.x == 0 && q == 0 && lane == 0) {
       dbg[12 + 4 * g] = a_s; dbg[13 + 4 * g] = a_c; dbg[14 + 4 * g] = a_o; dbg[15 + 4 * g] = a_e;
     }

@@ -108,6 +108,7 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt16SmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
       attr = true;
@@ -141,8 +142,30 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     } else {
       const char* e = getenv("EFFOCR_ATT_DBG_PTR");  // tools/att_timeline.py: device buffer of 32 int64 receiving wait-time totals
       long long* dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
-      if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, dbg);
-      else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, nullptr);
+      // output tile as a 4-D tensor {D, 197 tokens, batch, 1}: a 32-token box that runs past token 196 is clipped
+      CUtensorMap to;
+      {
+        const uint64_t dims[4] = {static_cast<uint64_t>(D), static_cast<uint64_t>(T), static_cast<uint64_t>(batch), 1};
+        const uint64_t strides[3] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(T) * D * 2, static_cast<uint64_t>(batch) * T * D * 2};
+        const uint32_t box[4] = {64, 32, 1, 1}, es[4] = {1, 1, 1, 1};
+        EFFOCR_TRY(make_tmap_4d(&to, out, 2, dims, strides, box, es, 128));
+      }
+      static const bool tma_out = [] {
+        const char* e = getenv("EFFOCR_ATT_TMA_OUT");  // "0" = per-thread row stores (A/B)
+        return !(e && e[0] == '0');
+      }();
+      const char* ab = getenv("EFFOCR_ATT_ABLATE");  // timing experiments (tools/att_ablate.py): results are wrong on purpose
+      const int abl = ab ? atoi(ab) : 0;
+#define EFFOCR_ATT_ABL(m)                                                                                              \
+  if (abl == m) {                                                                                                      \
+    EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false, m, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes)); \
+    attention_tc2b_kernel<false, m, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);        \
+  } else
+      EFFOCR_ATT_ABL(1) EFFOCR_ATT_ABL(2) EFFOCR_ATT_ABL(4) EFFOCR_ATT_ABL(8) EFFOCR_ATT_ABL(3) EFFOCR_ATT_ABL(7) EFFOCR_ATT_ABL(15)
+#undef EFFOCR_ATT_ABL
+      if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, dbg);
+      else if (!tma_out) attention_tc2b_kernel<false, 0, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);
+      else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);
     }
   }
   EFFOCR_CUDA(cudaGetLastError());
