@@ -253,14 +253,19 @@ def time_pipeline_c3(args, rec_pipe, rank, barrier):
     chars = [chr(33 + i % 94) for i in range(rec_pipe.index.ntotal)]
     full = EffOCRPipeline(loc, rec_pipe, chars, lang="en", knn=1)
     run_effocr(lines[:2 * bl], full, batch_lines=bl)  # warm-up, through the overlapped two-batch path
-    barrier()
-    t0 = time.perf_counter()
-    res = []
     overlap = os.environ.get("EFFOCR_PIPELINE_OVERLAP", "1") != "0"  # A/B switch for the two-stream software pipeline
-    for batch_res in full.infer_batches((lines[i0:i0 + bl] for i0 in range(0, L, bl)), overlap=overlap):
-        res += batch_res
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    # wall clock over host + device work: three passes over the same lines, the median is reported (one pass is 0.2 s and a
+    # single host hiccup -- page faults, a neighbour on the box -- otherwise decides the number); all three are listed
+    passes = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        res = []
+        for batch_res in full.infer_batches((lines[i0:i0 + bl] for i0 in range(0, L, bl)), overlap=overlap):
+            res += batch_res
+        torch.cuda.synchronize()
+        passes.append(time.perf_counter() - t0)
+    dt = sorted(passes)[1]
     ncrops = sum(len(r["char_boxes"]) for r in res)
     # localizer stage alone (device letterbox + YOLOv5s + NMS + boxes to host)
     torch.cuda.synchronize()
@@ -269,7 +274,7 @@ def time_pipeline_c3(args, rec_pipe, rank, barrier):
         full.localize(lines[i0:i0 + bl])
     torch.cuda.synchronize()
     dl = time.perf_counter() - t1
-    return {"lines": L, "crops": ncrops, "seconds": dt, "localizer_seconds": dl, "conf_thresh": hi}
+    return {"lines": L, "crops": ncrops, "seconds": dt, "pass_seconds": passes, "localizer_seconds": dl, "conf_thresh": hi}
 
 
 def main():
@@ -423,10 +428,13 @@ def main():
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         sec, lsec = float(agg[0]), float(agg[1])
         nl, nc = float(tot[0]), float(tot[1])
+        pass_seconds = pipe_block["pass_seconds"]
         pipe_block = {"workload": "config C3: YOLOv5s localizer (640x640 letterbox, iou 0.01) + ViT-S/16 + kNN k=1 on synthetic "
                                   f"64x1024 lines, {args.pipeline_lines} lines per GPU, host u8 lines in / strings out",
                       "lines": int(nl), "crops": int(nc), "crops_per_line": nc / max(nl, 1), "lines_per_s": nl / sec,
-                      "crops_per_s": nc / sec, "localizer_lines_per_s": nl / lsec, "timing": "wall clock, max over ranks",
+                      "crops_per_s": nc / sec, "localizer_lines_per_s": nl / lsec,
+                      "timing": "wall clock, median of three passes, max over ranks",
+                      "rank0_pass_lines_per_s": [pipe_block["lines"] / t for t in pass_seconds],
                       "conf_thresh_calibrated": pipe_block["conf_thresh"]}
     total_crops = B * world * args.steps
     value = total_crops / (ms_dev / 1e3)

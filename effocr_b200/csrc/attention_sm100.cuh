@@ -720,6 +720,11 @@ __device__ __forceinline__ void at_tma_store_4d(const CUtensorMap* m, const void
                "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// 16-byte store to shared memory by 32-bit shared address (the generic-pointer form compiles to ST.E.128 with 64-bit
+// address arithmetic per store)
+__device__ __forceinline__ void at_sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void at_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void at_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void at_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -916,6 +921,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * kAtTmemRegion;
     uint8_t* pmain = smem_p + g * kAtPBytes + r * 128;
     uint8_t* ptail = smem_p + g * kAtPBytes + kAtPMain + r * 32;
+    const uint32_t pmain_s = smem_u32(pmain), ptail_s = smem_u32(ptail);
     auto ex2x = [&](float x) { return (kAblate & 4) ? fmaf(x, 0.001f, 0.5f) : ex2_approx(x); };
     int it = 0;
     long long a_s = 0, a_c = 0, a_o = 0, a_e = 0;  // dbg: cycles in the s_full wait / softmax / o_full wait / epilogue
@@ -959,13 +965,13 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
             s4[(2 * t + 1) & 3] += p1;
             ph[t] = __floats2half2_rn(p0, p1);
           }
-          uint8_t* chunk = pmain + (c >> 2) * kAtQBytes;
+          const uint32_t chunk = pmain_s + (c >> 2) * kAtQBytes;
           const int piece = (c & 3) * 2;
           if (!(kAblate & 2)) {
-            *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
-            *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+            at_sts128(chunk + ((piece ^ (r & 7)) << 4), pk[0]);
+            at_sts128(chunk + (((piece + 1) ^ (r & 7)) << 4), pk[1]);
           } else if (pk[0].x == 0x12345u) {
-            *reinterpret_cast<uint4*>(chunk) = pk[1];
+            at_sts128(chunk, pk[1]);
           }
         }
         lA = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -1004,13 +1010,13 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
           if (kAblate & 2) {
             if (pk[0].x == 0x12345u) *reinterpret_cast<uint4*>(pmain) = pk[1];
           } else if (c < 4) {
-            uint8_t* chunk = pmain + 2 * kAtQBytes;
+            const uint32_t chunk = pmain_s + 2 * kAtQBytes;
             const int piece = c * 2;
-            *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 4)) = pk[0];
-            *reinterpret_cast<uint4*>(chunk + (((piece + 1) ^ (r & 7)) << 4)) = pk[1];
+            at_sts128(chunk + ((piece ^ (r & 7)) << 4), pk[0]);
+            at_sts128(chunk + (((piece + 1) ^ (r & 7)) << 4), pk[1]);
           } else {
-            *reinterpret_cast<uint4*>(ptail + ((0 ^ ((r >> 2) & 1)) << 4)) = pk[0];  // SWIZZLE_32B: bit 4 ^= bit 7
-            *reinterpret_cast<uint4*>(ptail + ((1 ^ ((r >> 2) & 1)) << 4)) = pk[1];
+            at_sts128(ptail_s + ((0 ^ ((r >> 2) & 1)) << 4), pk[0]);  // SWIZZLE_32B: bit 4 ^= bit 7
+            at_sts128(ptail_s + ((1 ^ ((r >> 2) & 1)) << 4), pk[1]);
           }
         }
         lB = (s4[0] + s4[1]) + (s4[2] + s4[3]);
@@ -1052,7 +1058,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
               ph[t] = __floats2half2_rn(fmaf(__uint_as_float(o1[e]), wA, __uint_as_float(o2[e]) * wB),
                                         fmaf(__uint_as_float(o1[e + 1]), wA, __uint_as_float(o2[e + 1]) * wB));
             }
-            if (kTmaOut) *reinterpret_cast<uint4*>(pmain + (((hh * 4 + j) ^ (r & 7)) << 4)) = pk;
+            if (kTmaOut) at_sts128(pmain_s + (((hh * 4 + j) ^ (r & 7)) << 4), pk);
             else if (!(kAblate & 1) || pk.x == 0x12345u) *reinterpret_cast<uint4*>(dst + hh * 32 + 8 * j) = pk;
           }
         }
