@@ -66,6 +66,23 @@ def test_vit_matches_torchvision():
     assert ((a - b).norm() / b.norm()).item() <= 5e-6
 
 
+def test_convnext_matches_torchvision():
+    """The ConvNeXt-Tiny restatement (timm keys, num_classes=0) against torchvision's convnext_tiny with the classifier's
+    Linear removed (avgpool -> LayerNorm2d -> flatten: the same pooled pre-logits), through oracle.convnext.timm_to_torchvision."""
+    from torchvision.models import convnext_tiny
+    from oracle import convnext as OC
+    sd = OC.init_convnext_tiny_state_dict(seed=4)
+    tv = convnext_tiny(weights=None)
+    tv.classifier[2] = torch.nn.Identity()
+    tv.load_state_dict(OC.timm_to_torchvision(sd), strict=True)
+    tv.eval()  # stochastic depth off
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        a, b = OC.convnext_forward(sd, x), tv(x)
+    assert a.shape == (2, 768)
+    assert ((a - b).norm() / b.norm()).item() <= 5e-6
+
+
 def test_vit_key_maps_roundtrip():
     sd = OV.init_vit_state_dict("vit_tiny_patch16_224", seed=0)
     back = OV.hf_to_timm(OV.timm_to_hf(sd))
