@@ -8,7 +8,7 @@ onnx_engines/recognizer_engine.py:27.  timm is an un-vendored, un-pinned depende
 plain torch ops on timm-keyed state dicts (`net.` prefix as saved by the reference,
 train_effocr_recognizer.py:65-72).
 
-Pinned (tests/test_oracle_vit.py) against
+Pinned (tests/test_oracle.py: test_vit_matches_golden_reference_hf_backend, test_vit_matches_torchvision) against
   * the reference's own "hf" back-end, run live: AutoEncoderFactory("hf", dir) (encoders.py:72-91)
     over a random-init transformers.ViTModel, weights mapped key-by-key, and
   * torchvision.models.vision_transformer.VisionTransformer with the same weights,

@@ -8,7 +8,7 @@ ultralytics/yolov5 is un-vendored and unpinned, so the published v6.x/7.0 `yolov
 state dict (`model.{i}....`), with BatchNorm (eps 1e-3) applied explicitly.
 
 PARITY UNPINNED against a second YOLOv5 implementation (none is installable here); pinned instead by
-analytic invariants the published model must satisfy (tests/test_oracle_yolo.py): 7 235 389
+analytic invariants the published model must satisfy (tests/test_oracle.py::test_yolov5s_analytic_invariants): 7 235 389
 parameters at nc = 80, 25 200 predictions at 640 x 640, fp64-vs-fp32 self-consistency.
 
 `letterbox` / `non_max_suppression` restate localizer_engine.py:107-138 / :171-277 and ARE pinned
