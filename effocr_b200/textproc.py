@@ -2,7 +2,7 @@
 
 These stay on the host in the reference too: they are
 O(chars per line) Python on a few dozen boxes.  Semantics follow the reference exactly; tests pin
-them against the live reference functions (tests/test_host_textproc.py, tests/golden/textproc.json).
+them against the live reference functions (tests/test_oracle.py::test_textproc_matches_golden, tests/golden/textproc_golden.json).
 """
 from __future__ import annotations
 
