@@ -154,7 +154,10 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
         const char* e = getenv("EFFOCR_ATT_TMA_OUT");  // "0" = per-thread row stores (A/B)
         return !(e && e[0] == '0');
       }();
-      const char* ab = getenv("EFFOCR_ATT_ABLATE");  // timing experiments (tools/att_ablate.py): results are wrong on purpose
+#ifdef EFFOCR_ATT_ABLATION
+      // timing experiments (tools/att_ablate.py): kernels whose results are wrong on purpose -- only in a library built with
+      // EFFOCR_NVCC_EXTRA=-DEFFOCR_ATT_ABLATION, never in the product build
+      const char* ab = getenv("EFFOCR_ATT_ABLATE");
       const int abl = ab ? atoi(ab) : 0;
 #define EFFOCR_ATT_ABL(m)                                                                                              \
   if (abl == m) {                                                                                                      \
@@ -163,6 +166,7 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
   } else
       EFFOCR_ATT_ABL(1) EFFOCR_ATT_ABL(2) EFFOCR_ATT_ABL(4) EFFOCR_ATT_ABL(8) EFFOCR_ATT_ABL(3) EFFOCR_ATT_ABL(7) EFFOCR_ATT_ABL(15)
 #undef EFFOCR_ATT_ABL
+#endif
       if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, dbg);
       else if (!tma_out) attention_tc2b_kernel<false, 0, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);
       else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);

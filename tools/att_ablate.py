@@ -1,5 +1,7 @@
 """Timing ablations of the default attention kernel (results are wrong on purpose): which part of the softmax warps' work sets
 the period.  EFFOCR_ATT_ABLATE bits: 1 no global stores, 2 no P stores, 4 no MUFU (FMA instead of ex2), 8 no maximum search.
+The ablated kernels are not part of the product library: build it first with
+  EFFOCR_NVCC_EXTRA=-DEFFOCR_ATT_ABLATION python -m effocr_b200.build --force   (and rebuild without it afterwards)
 usage (GPU box): PYTHONPATH=. python tools/att_ablate.py"""
 import os
 import sys
