@@ -20,7 +20,8 @@ ROOT = Path(__file__).resolve().parent.parent
 G, P = ROOT / "gpurun_out", ROOT / "profiles"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
-for src, dst in (("bench.json", f"{tag}_bench.json"), ("bench_reference.json", f"{tag}_bench_reference.json")):
+for src, dst in (("bench.json", f"{tag}_bench.json"), ("bench_reference.json", f"{tag}_bench_reference.json"),
+                 ("att_timeline.txt", f"{tag}_att_timeline_latest.txt")):
     if (G / src).exists() and (G / src).stat().st_size:
         shutil.copy(G / src, P / dst)
 

@@ -22,4 +22,6 @@ timeout 900 ncu --set full --clock-control none --import-source on \
 timeout 600 ncu --set full --clock-control none --import-source on \
     -k regex:"crop_resize|knn_" -c 8 -f -o $O/misc_full \
     python tools/profile_misc.py > $O/ncu_misc.log 2>&1; echo "rc=$?"
+echo "== attention wait-time timeline"
+PYTHONPATH=. timeout 120 python tools/att_timeline.py 0 > $O/att_timeline.txt 2>&1; echo "rc=$?"
 ls -la $O
