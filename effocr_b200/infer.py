@@ -183,9 +183,16 @@ class EffOCRPipeline:
         batch i fetched and decoded.  (A worker thread was tried first: the two Python threads fought over the GIL
         and the pipeline got slower.)  Results are identical to the sequential order: the stages share no mutable
         state and every kernel is deterministic."""
-        batches = [b for b in batches]
-        if not overlap or len(batches) < 2:
-            for chunk in batches:
+        # `batches` is consumed lazily, one batch ahead of the one being recognised, so that a decoding iterator
+        # (effocr_b200.lineio.LineDecoder) keeps working while the GPU does
+        it = iter(batches)
+        first = next(it, None)
+        if first is None:
+            return
+        second = next(it, None) if overlap else None
+        if second is None:  # sequential order (also: a single batch)
+            yield self.infer_lines(first)
+            for chunk in it:
                 yield self.infer_lines(chunk)
             return
         side = getattr(self, "_side_stream", None)  # persistent: the caching allocator keeps one block pool per stream
@@ -198,12 +205,14 @@ class EffOCRPipeline:
             with torch.cuda.stream(side):
                 return self.stage_localize(chunk)
 
-        st = stage1(batches[0])
-        for i in range(len(batches)):
+        st, nxt = stage1(first), second
+        while True:
             idx = self.launch_recognize(st) if st is not None else None
-            st_next = stage1(batches[i + 1]) if i + 1 < len(batches) else None
+            st_next = stage1(nxt) if nxt is not None else None
             yield self.finish_recognize(st, idx) if st is not None else []
-            st = st_next
+            if nxt is None:
+                break
+            st, nxt = st_next, next(it, None)
 
 
 def run_effocr_sharded(images_rgb, pipeline, keys=None, batch_lines: int = 64, weights=None):
