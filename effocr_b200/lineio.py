@@ -120,14 +120,10 @@ def mmdet_output_format(result):
     return [[chars, words]] if words else [[chars]]
 
 
-def run_effocr_paths(paths, pipeline, batch_lines: int = 64, workers: int | None = None, prefetch: int = 2,
-                     overlap: bool = True, lang: str | None = None, decode=decode_rgb):
-    """Decode, localise, recognise: -> (inference_results {path: text}, inference_coco), the pair the reference's
-    `run_effocr` returns (infer_effocr_onnx_multi.py:397).  Lines without a detected character are left out of
-    inference_results, as `if output is None: continue` does (infer_effocr.py:551-552).  For Japanese the COCO
-    structure carries one image entry per line (with its transcription) and one annotation per character box whose
-    `text` is the string of its k nearest glyphs (infer_effocr.py:554-559); image ids count the recognised lines."""
-    lang = lang if lang is not None else getattr(pipeline, "lang", "en")
+def transcribe_paths(paths, pipeline, batch_lines: int = 64, workers: int | None = None, prefetch: int = 2,
+                     overlap: bool = True, decode=decode_rgb):
+    """Decode, localise, recognise: -> one record (path, height, width, per-line result dict) per input line, in input
+    order.  The decoder runs one batch ahead of `pipeline.infer_batches`, which pulls its batches lazily."""
     decoder = LineDecoder(paths, batch_lines=batch_lines, workers=workers, prefetch=prefetch, decode=decode)
     chunks, shapes = [], []
 
@@ -141,23 +137,66 @@ def run_effocr_paths(paths, pipeline, batch_lines: int = 64, workers: int | None
         results = pipeline.infer_batches(batches(), overlap=overlap)
     else:  # any object with infer_lines() works as a pipeline
         results = map(pipeline.infer_lines, batches())
+    records = []
+    for b, res in enumerate(results):
+        records += [(path, int(h), int(w), r) for path, (h, w), r in zip(chunks[b], shapes[b], res)]
+        chunks[b] = shapes[b] = None  # keep the bookkeeping of finished batches small
+    return records
+
+
+def assemble_results(records, lang: str = "en"):
+    """Records in input order -> (inference_results {path: text}, inference_coco), the pair the reference's `run_effocr`
+    returns (infer_effocr_onnx_multi.py:397).  Lines without a detected character are left out of inference_results, as
+    `if output is None: continue` does (infer_effocr.py:551-552).  For Japanese the COCO structure carries one image
+    entry per line (with its transcription) and one annotation per character box whose `text` is the string of its k
+    nearest glyphs (infer_effocr.py:554-559); image ids count the recognised lines."""
     inference_results = {}
     inference_coco = copy.deepcopy(COCO_JSON_SKELETON)
     image_id = anno_id = 0
-    for b, res in enumerate(results):
-        for path, (h, w), r in zip(chunks[b], shapes[b], res):
-            if r["text"] is None:
-                continue
-            if lang == "jp":
-                inference_coco["images"].append(create_coco_image_entry(os.path.basename(path), h, w, image_id, text=r["text"]))
-                for nn_chars, box in zip(r.get("nns", []), r.get("char_boxes", [])):
-                    x0, y0, x1, y1 = (int(round(v)) for v in box[:4])
-                    inference_coco["annotations"].append(
-                        create_coco_anno_entry(x0, y0, x1 - x0, y1 - y0, anno_id, image_id, cat_id=0, text=nn_chars))
-            inference_results[path] = r["text"]
-            image_id += 1
-        chunks[b] = shapes[b] = None  # keep the bookkeeping of finished batches small
+    for path, h, w, r in records:
+        if r["text"] is None:
+            continue
+        if lang == "jp":
+            inference_coco["images"].append(create_coco_image_entry(os.path.basename(path), h, w, image_id, text=r["text"]))
+            for nn_chars, box in zip(r.get("nns", []), r.get("char_boxes", [])):
+                x0, y0, x1, y1 = (int(round(v)) for v in box[:4])
+                inference_coco["annotations"].append(
+                    create_coco_anno_entry(x0, y0, x1 - x0, y1 - y0, anno_id, image_id, cat_id=0, text=nn_chars))
+        inference_results[path] = r["text"]
+        image_id += 1
     return inference_results, inference_coco
+
+
+def run_effocr_paths(paths, pipeline, batch_lines: int = 64, workers: int | None = None, prefetch: int = 2,
+                     overlap: bool = True, lang: str | None = None, decode=decode_rgb):
+    """One process, one GPU: `assemble_results(transcribe_paths(...))`."""
+    lang = lang if lang is not None else getattr(pipeline, "lang", "en")
+    return assemble_results(transcribe_paths(paths, pipeline, batch_lines, workers, prefetch, overlap, decode), lang)
+
+
+def run_effocr_paths_sharded(paths, pipeline, batch_lines: int = 64, workers: int | None = None, prefetch: int = 2,
+                             overlap: bool = True, lang: str | None = None, decode=decode_rgb, weights=None, dst: int = 0):
+    """Data-parallel over lines: rank r decodes and transcribes the paths
+    `dist.shard_indices` gives it (strided, or balanced by `weights`, e.g. file sizes), the per-line records travel to
+    rank `dst` in one `gather_object`, and the result pair is assembled there in INPUT order -- identical to the
+    single-process output whatever the world size.  Other ranks return (None, None).  No steady-state collective."""
+    import torch.distributed as tdist
+
+    from . import dist as D
+
+    rank, world, _ = D.init_from_env()
+    lang = lang if lang is not None else getattr(pipeline, "lang", "en")
+    paths = list(paths)
+    mine = D.shard_indices(len(paths), rank, world, weights=weights)
+    local = transcribe_paths([paths[i] for i in mine], pipeline, batch_lines, workers, prefetch, overlap, decode)
+    if world == 1:
+        return assemble_results(local, lang)
+    parts = [None] * world if rank == dst else None
+    tdist.gather_object(list(zip(mine, local)), parts, dst=dst)
+    if rank != dst:
+        return None, None
+    merged = sorted((item for part in parts for item in part), key=lambda t: t[0])
+    return assemble_results([rec for _, rec in merged], lang)
 
 
 def save_output(save_dir: str, paths, inference_results, inference_coco, copy_images: bool = True) -> None:

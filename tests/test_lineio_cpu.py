@@ -211,3 +211,41 @@ def test_infer_batches_consumes_lazily_and_matches_sequential(monkeypatch):
     assert seq == out
     assert list(P().infer_batches(iter([]), overlap=True)) == []
     assert list(P().infer_batches(iter([[7]]), overlap=True)) == [["r7"]]
+
+
+def _sharded_worker(rank, world, port, q, paths):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from effocr_b200 import dist as D
+    from effocr_b200 import lineio as L
+    D.init_from_env("gloo")
+    pipe = _FakePipeline()
+    sizes = [os.path.getsize(p) for p in paths]
+    out = L.run_effocr_paths_sharded(paths, pipe, batch_lines=2, workers=2, weights=sizes if rank >= 0 else None)
+    q.put((rank, out, sum(pipe.calls)))
+    torch.distributed.destroy_process_group()
+
+
+def test_run_effocr_paths_sharded_two_ranks_equals_single_process(tmp_path):
+    """world_size 2 over gloo: every rank decodes and transcribes its shard only; rank 0 assembles results and the COCO
+    structure in input order -- equal to the single-process pair (ids included)."""
+    import socket
+    import torch.multiprocessing as mp
+    paths, _ = _write_lines(tmp_path, 9)
+    single = lineio.run_effocr_paths(paths, _FakePipeline(), batch_lines=4)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q, paths)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+    (_, out0, n0), (_, out1, n1) = res
+    assert out1 == (None, None)
+    assert n0 + n1 == len(paths) and 0 < n0 < len(paths)  # the lines were split, none transcribed twice
+    assert out0[0] == single[0] and list(out0[0]) == list(single[0])
+    assert out0[1] == single[1]
