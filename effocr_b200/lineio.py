@@ -107,6 +107,50 @@ class LineDecoder:
                 yield chunk, images
 
 
+IMG_EXTENSIONS = (".jpg", ".jpeg", ".png", ".ppm", ".bmp", ".pgm", ".tif", ".tiff", ".webp")  # torchvision ImageFolder
+
+
+def render_dataset_files(root_dir: str, font_name: str = ""):
+    """The files `create_render_dataset(root_dir, lang, font_name=...)` embeds for an ad-hoc index
+    (effocr_datasets/recognizer_datasets.py:213-223): a torchvision ImageFolder walk of root_dir -- class directories in
+    sorted order, inside each every image file below it in sorted walk order -- keeping the paths that contain
+    `font_name` and whose basename does not start with "PAIRED" (those are scanned crops, not renders)."""
+    classes = sorted(e.name for e in os.scandir(root_dir) if e.is_dir())
+    files = []
+    for cls in classes:
+        for base, _dirs, names in sorted(os.walk(os.path.join(root_dir, cls), followlinks=True)):
+            for name in sorted(names):
+                if name.lower().endswith(IMG_EXTENSIONS):
+                    files.append(os.path.join(base, name))
+    return [p for p in files if font_name in p and not os.path.basename(p).startswith("PAIRED")]
+
+
+def chars_from_render_files(files):
+    """One candidate character per render file (infer_effocr.py:197-198): `0x<hex>_...` names give chr(hex), any other
+    name gives its first character."""
+    out = []
+    for p in files:
+        name = os.path.basename(p)
+        out.append(chr(int(name.split("_")[0], base=16)) if name.startswith("0x") else name[0])
+    return out
+
+
+def build_ad_hoc_index(root_dir: str, recognizer, lang: str = "en", font_name: str | None = None, decode=decode_rgb,
+                       workers: int | None = None):
+    """`--ad_hoc_index_root_dir` (infer_effocr.py:190-201): embed the rendered glyphs of one font on the device and make
+    them the recognizer's index; returns the candidate characters.  Default font as in the reference:
+    NotoSerifCJKjp-Regular for jp, NotoSerif-Regular otherwise.  `recognizer` is a `pipeline.RecognizerPipeline`."""
+    if font_name is None:
+        font_name = "NotoSerifCJKjp-Regular" if lang == "jp" else "NotoSerif-Regular"
+    files = render_dataset_files(root_dir, font_name)
+    if not files:
+        raise ValueError(f"no rendered glyphs of font {font_name!r} below {root_dir}")
+    chars = chars_from_render_files(files)
+    glyphs = [im for _, images in LineDecoder(files, batch_lines=256, workers=workers, decode=decode) for im in images]
+    recognizer.train_knn(glyphs, candidate_chars=chars)
+    return chars
+
+
 def mmdet_output_format(result):
     """Detectron2-style predictions -> the mmdet-style nesting the reference's pre-processing expects
     (infer_effocr.py:245-254): [[char_boxes]] or [[char_boxes, word_boxes]], each box [x0, y0, x1, y1, score];

@@ -79,6 +79,32 @@ class RecognizerPipeline:
             self.encoder.forward(None, batch=b, out=out[b0:b0 + b])
         return ops.l2_normalize(out)
 
+    def embed_crops(self, crops) -> torch.Tensor:
+        """crops: list of u8 [h, w, 3] arrays (each taken whole) -> L2-normalised embeddings, CUDA f32 [n, D]; chunks of
+        max_batch through the same crop kernel and encoder as recognition (the composition bench.py builds its
+        10 000-glyph index with)."""
+        out = torch.empty((len(crops), self.encoder.embed_dim), device="cuda", dtype=torch.float32)
+        for i0 in range(0, len(crops), self.max_batch):
+            pixels, images, boxes, n = PackedCrops(crops[i0:i0 + self.max_batch]).to_device()
+            out[i0:i0 + n] = self.embed_boxes(pixels, images, boxes, n)
+        return out
+
+    def train_knn(self, glyph_crops, candidate_chars=None) -> None:
+        """Index construction on the device: what `InferenceModel.train_knn(render_dataset)`
+        does in the reference (infer_effocr.py:190-201: paired transform on the host per glyph, trunk forward in batches
+        of 64, `IndexFlatIP.add`) -- here the rendered glyph images go through the fused crop kernel and the encoder in
+        batches of max_batch and the normalised prototypes REPLACE the index; `candidate_chars` (one per glyph) replaces
+        the label list when given."""
+        vectors = self.embed_crops(list(glyph_crops))
+        index = FlatIPIndex(self.encoder.embed_dim)
+        index.add(vectors)
+        self.index = index
+        if candidate_chars is not None:
+            candidate_chars = list(candidate_chars)
+            if len(candidate_chars) != index.ntotal:
+                raise ValueError(f"{len(candidate_chars)} candidate chars for {index.ntotal} glyph renders")
+            self.candidate_chars = candidate_chars
+
     def recognize_device(self, pixels, images, boxes, n: int, k: int = 10):
         emb = self.embed_boxes(pixels, images, boxes, n)
         dist, idx = self.index.search_device(emb, k)

@@ -249,3 +249,40 @@ def test_run_effocr_paths_sharded_two_ranks_equals_single_process(tmp_path):
     assert n0 + n1 == len(paths) and 0 < n0 < len(paths)  # the lines were split, none transcribed twice
     assert out0[0] == single[0] and list(out0[0]) == list(single[0])
     assert out0[1] == single[1]
+
+
+def test_render_dataset_files_match_torchvision_imagefolder_and_chars(tmp_path):
+    """File selection and order of the ad-hoc index = the reference's FontImageFolder (a torchvision ImageFolder walk)
+    filtered by font name / PAIRED prefix; characters parsed from the file names as infer_effocr.py:197-198 does."""
+    from PIL import Image
+    from torchvision.datasets import ImageFolder
+    layout = {
+        "0x41": ["0x41_NotoSerif-Regular.png", "0x41_Other-Font.png", "PAIRED_0x41_NotoSerif-Regular_3.png"],
+        "0x3042": ["0x3042_NotoSerifCJKjp-Regular.png", "0x3042_NotoSerif-Regular.jpg"],
+        "b": ["b_NotoSerif-Regular.png", "notes.txt"],
+        "0x42": ["sub/0x42_NotoSerif-Regular.png"],
+    }
+    for cls, names in layout.items():
+        for n in names:
+            p = tmp_path / cls / n
+            p.parent.mkdir(parents=True, exist_ok=True)
+            if n.endswith(".txt"):
+                p.write_text("x")
+            else:
+                Image.fromarray(np.zeros((5, 5, 3), np.uint8)).save(p)
+    font = "NotoSerif-Regular"
+    got = lineio.render_dataset_files(str(tmp_path), font)
+    ref = [p for p, _ in ImageFolder(str(tmp_path)).samples if font in p and not os.path.basename(p).startswith("PAIRED")]
+    assert got == ref and len(got) == 4
+    assert lineio.chars_from_render_files(got) == ["あ", "A", "B", "b"]
+    assert lineio.render_dataset_files(str(tmp_path), "NotoSerifCJKjp-Regular") == [str(tmp_path / "0x3042" / "0x3042_NotoSerifCJKjp-Regular.png")]
+
+    class Rec:  # stands in for RecognizerPipeline: records what build_ad_hoc_index hands over
+        def train_knn(self, glyphs, candidate_chars=None):
+            self.shapes, self.chars = [g.shape for g in glyphs], candidate_chars
+
+    rec = Rec()
+    chars = lineio.build_ad_hoc_index(str(tmp_path), rec, lang="en")
+    assert chars == rec.chars == ["あ", "A", "B", "b"] and rec.shapes == [(5, 5, 3)] * 4
+    with pytest.raises(ValueError):
+        lineio.build_ad_hoc_index(str(tmp_path), rec, lang="en", font_name="NoSuchFont")
