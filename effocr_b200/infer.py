@@ -41,15 +41,19 @@ def crop_rects_onnx_path(bboxes, im_height: int, im_width: int, vertical: bool):
     rescale in float64 in the reference's operation order ((x * extent) / 640), np.rint == Python round()."""
     if len(bboxes) == 0:
         return []
-    b = bboxes.numpy() if isinstance(bboxes, torch.Tensor) else np.asarray([np.asarray(v, dtype=np.float32) for v in bboxes])
-    r = np.rint(b[:, :4].astype(np.float32)).astype(np.float64)
+    if isinstance(bboxes, torch.Tensor):
+        b = bboxes.numpy()
+    elif isinstance(bboxes, np.ndarray) and bboxes.ndim == 2:
+        b = bboxes
+    else:
+        b = np.asarray([np.asarray(v, dtype=np.float32) for v in bboxes])
+    k = (1, 3) if vertical else (0, 2)
+    extent = im_height if vertical else im_width
+    r = np.rint(b[:, k].astype(np.float32, copy=False)).astype(np.float64)
+    lo, hi = np.rint(r * extent / 640).astype(np.int64).T.tolist()
     if vertical:
-        y0 = np.rint(r[:, 1] * im_height / 640).astype(np.int64)
-        y1 = np.rint(r[:, 3] * im_height / 640).astype(np.int64)
-        return [(0, int(a), im_width, int(c)) for a, c in zip(y0, y1)]
-    x0 = np.rint(r[:, 0] * im_width / 640).astype(np.int64)
-    x1 = np.rint(r[:, 2] * im_width / 640).astype(np.int64)
-    return [(int(a), 0, int(c), im_height) for a, c in zip(x0, x1)]
+        return [(0, a, im_width, c) for a, c in zip(lo, hi)]
+    return [(a, 0, c, im_height) for a, c in zip(lo, hi)]
 
 
 def crop_rect_torch_path(bbox, im_height: int, im_width: int, vertical: bool, double_clipped: bool = True):
@@ -106,14 +110,14 @@ class EffOCRPipeline:
         if self.lang == "en":
             char_b, word_b = bboxes[labels == 0], bboxes[labels == 1]
             if len(char_b) != 0:
-                char_b, word_end_idx = textproc.en_preprocess(char_b, word_b)
+                char_b, word_end_idx = textproc.en_preprocess_np(char_b, word_b)  # == en_preprocess, vectorised
         else:
             char_b = bboxes[labels == 0]
-            if len(char_b) != 0:
-                char_b = textproc.jp_preprocess(char_b, vertical=self.vertical)
+            if len(char_b) != 0:  # jp_preprocess: stable sort along the text direction
+                char_b = char_b[np.argsort(char_b[:, 1 if self.vertical else 0], kind="stable")]
         rects = crop_rects_onnx_path(char_b, im_h, im_w, self.vertical)
-        heights = [b[3] - b[1] for b in char_b]
-        bottoms = [b[3] for b in char_b]
+        heights = list(char_b[:, 3] - char_b[:, 1])  # float32 scalars, as b[3] - b[1] row by row
+        bottoms = list(char_b[:, 3])
         return list(char_b), word_end_idx, rects, heights, bottoms
 
     # -- the two GPU phases as separately schedulable stages (run_effocr overlaps stage 1 of batch i+1 with stage 2 of batch i)

@@ -64,6 +64,41 @@ def en_preprocess(bboxes_char, bboxes_word, vertical: bool = False, score_thresh
     return sorted_char, word_end_idx
 
 
+def en_preprocess_np(char_boxes, word_boxes, vertical: bool = False):
+    """`en_preprocess` of the ONNX path (no score filtering) on float32 arrays [n, >=4] / [w, >=4], vectorised: the same
+    stable ordering and, per word, the same float32 `abs(wordleft - charright)` values, strict `<` (first minimum wins),
+    `charright > wordleft` filter, 1e6 starting distance and carry-over of the previous word's index as the scalar
+    loop above -- one [w, n] array operation instead of w * n Python iterations on numpy scalars.
+    -> (char boxes sorted along the text direction [n, :], word_end_idx list)."""
+    import numpy as np
+
+    char_boxes = np.asarray(char_boxes, dtype=np.float32)
+    word_boxes = np.asarray(word_boxes, dtype=np.float32)
+    if char_boxes.ndim != 2:
+        char_boxes = char_boxes.reshape(-1, 4)
+    if word_boxes.ndim != 2:
+        word_boxes = word_boxes.reshape(-1, 4)
+    k = 1 if vertical else 0
+    sorted_char = char_boxes[np.argsort(char_boxes[:, k], kind="stable")] if len(char_boxes) else char_boxes
+    if len(word_boxes) == 0:
+        return sorted_char, []
+    sorted_word = word_boxes[np.argsort(word_boxes[:, k], kind="stable")]
+    word_end_idx, closest_idx = [], 0
+    if len(sorted_char):
+        rights, lefts = sorted_char[:, 2], sorted_word[:, 0]
+        dist = np.abs(lefts[:, None] - rights[None, :])  # float32, as the scalar subtraction
+        ok = (rights[None, :] > lefts[:, None]) & (dist < np.float32(LARGE_NUMBER))
+        best = np.where(ok, dist, np.float32(np.inf)).argmin(axis=1)  # first index of the minimum
+        found = ok.any(axis=1)
+        for j in range(len(sorted_word)):
+            if found[j]:
+                closest_idx = int(best[j])
+            word_end_idx.append(closest_idx)
+    else:
+        word_end_idx = [0] * len(sorted_word)
+    return sorted_char, word_end_idx
+
+
 def jp_preprocess(bboxes_char, vertical: bool = True, score_thresh=None):
     """infer_effocr_onnx_multi.py:134-140 / infer_effocr.py:413-419."""
     sorted_char = sorted(bboxes_char, key=_key(vertical))
@@ -80,9 +115,21 @@ def en_postprocess(line_output, word_end_idx, charheights, charbottoms, anchor_m
         f"{len(line_output)} == {len(charheights)} == {len(charbottoms)}; {line_output}; {charbottoms}; {charheights}"
     if any(map(lambda x: len(x) == 0, (line_output, word_end_idx, charheights, charbottoms))):
         return None
-    outchars_w_spaces = [" " + x if idx in word_end_idx else x for idx, x in enumerate(line_output)]
-    charheights_w_spaces = list(flatten([(LARGE_NUMBER, x) if idx in word_end_idx else x for idx, x in enumerate(charheights)]))
-    charbottoms_w_spaces = list(flatten([(0, x) if idx in word_end_idx else x for idx, x in enumerate(charbottoms)]))
+    ends = set(word_end_idx)
+    outchars_w_spaces = [" " + x if idx in ends else x for idx, x in enumerate(line_output)]
+    if anchor_margin is None and spell_checker is None and all(isinstance(x, str) and len(x) == 1 and not x.isspace() for x in line_output):
+        # fast path of the ONNX driver's call (single non-blank characters, no height rules): the two *_w_spaces lists are
+        # only length-checked below, and their length is n + (inserted markers) - (a leading marker, dropped)
+        # (the reference's length assertion can only trip when the first height equals the marker value itself)
+        assert 0 in ends or charheights[0] != LARGE_NUMBER, f"charheights = {charheights}; output = {line_output}"
+        return "".join(outchars_w_spaces).strip()
+    charheights_w_spaces, charbottoms_w_spaces = [], []
+    for idx, (hgt, bot) in enumerate(zip(charheights, charbottoms)):
+        if idx in ends:
+            charheights_w_spaces.append(LARGE_NUMBER)
+            charbottoms_w_spaces.append(0)
+        charheights_w_spaces += list(flatten([hgt])) if isinstance(hgt, (list, tuple)) else [hgt]
+        charbottoms_w_spaces += list(flatten([bot])) if isinstance(bot, (list, tuple)) else [bot]
     charbottoms_w_spaces = charbottoms_w_spaces[1:] if charbottoms_w_spaces[0] == 0 else charbottoms_w_spaces
     charheights_w_spaces = charheights_w_spaces[1:] if charheights_w_spaces[0] == LARGE_NUMBER else charheights_w_spaces
     line_output = "".join(outchars_w_spaces).strip()

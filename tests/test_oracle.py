@@ -213,3 +213,49 @@ def test_pack_images_layout_and_pool_reuse():
             assert o % 256 == 0 and (d["height"], d["width"], d["pitch"]) == (im.shape[0], im.shape[1], im.shape[1] * 3)
             assert np.array_equal(pixels.numpy()[o:o + im.size].reshape(im.shape), im)
     assert len(pool._bufs) <= 1 or not torch.cuda.is_available()
+
+
+def test_en_preprocess_np_equals_scalar_version():
+    """The vectorised word-end search the pipeline uses must return exactly what the (golden-pinned) scalar en_preprocess
+    returns: golden cases, random float32 boxes, exact ties, words left of / right of every character (index carry-over),
+    no words, no characters."""
+    from effocr_b200 import textproc as tp
+    cases = [(np.asarray(c["chars"], np.float32).reshape(-1, 4), np.asarray(c["words"], np.float32).reshape(-1, 4)) for c in MG.textproc_cases()]
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        n, w = int(rng.integers(0, 40)), int(rng.integers(0, 9))
+        x0 = rng.uniform(0, 640, n).astype(np.float32)
+        ch = np.stack([x0, rng.uniform(0, 60, n), x0 + rng.uniform(1, 40, n), rng.uniform(60, 64, n)], 1).astype(np.float32) if n else np.zeros((0, 4), np.float32)
+        wx = rng.uniform(-50, 700, w).astype(np.float32)
+        wd = np.stack([wx, np.zeros(w), wx + 80, np.full(w, 64.0)], 1).astype(np.float32) if w else np.zeros((0, 4), np.float32)
+        if n > 3 and w > 1:  # exact ties: duplicated boxes, a word edge exactly on / halfway between character edges
+            ch[1] = ch[0]
+            ch[3, 2] = ch[2, 2]
+            wd[0, 0] = ch[2, 2]
+            wd[1, 0] = np.float32((ch[0, 2] + ch[2, 2]) / 2)
+        cases.append((ch, wd))
+    for vertical in (False, True):
+        for ch, wd in cases:
+            sc, wei = tp.en_preprocess(list(ch), list(wd), vertical=vertical)
+            sc2, wei2 = tp.en_preprocess_np(ch, wd, vertical=vertical)
+            assert wei2 == wei
+            assert len(sc2) == len(sc) and all(np.array_equal(a, b) for a, b in zip(sc, sc2))
+
+
+def test_vectorised_crop_rects_equal_scalar_reference_semantics():
+    """infer.crop_rects_onnx_path (all boxes of a line at once; array, tensor and list input) == the scalar restatement
+    of infer_effocr_onnx_multi.py:311-318 box by box, half-way cases included, both text directions."""
+    from effocr_b200 import infer
+    rng = np.random.default_rng(3)
+    for (h, w) in [(64, 1024), (37, 640), (900, 55)]:
+        b = rng.uniform(-5, 660, (200, 4)).astype(np.float32)
+        b[::7] = np.round(b[::7]) + 0.5  # ties for round-half-to-even
+        b[::11, 0] = np.float32(0.8 * 3)  # products that land on x.5 after the rescale
+        for vertical in (False, True):
+            exp = [infer.crop_rect_onnx_path(row, h, w, vertical) for row in b]
+            assert [OT.crop_rect_onnx_path(list(map(float, row)), h, w, vertical=vertical) for row in b[:50]] == exp[:50]
+            assert infer.crop_rects_onnx_path(b, h, w, vertical) == exp
+            assert infer.crop_rects_onnx_path(torch.from_numpy(b), h, w, vertical) == exp
+            assert infer.crop_rects_onnx_path(list(b), h, w, vertical) == exp
+            assert all(type(v) is int for r in infer.crop_rects_onnx_path(b, h, w, vertical) for v in r)
+    assert infer.crop_rects_onnx_path(np.zeros((0, 4), np.float32), 64, 1024, False) == []
