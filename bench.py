@@ -8,8 +8,8 @@ Workload (BASELINE.json configs[1], the configuration the metric's target is quo
   exact inner-product top-10 against the index.
 
   value : whole-job crops/s with the u8 crops already resident in HBM (CUDA events, max over ranks)
-  e2e   : the same through RecognizerPipeline.recognize_stream() with HOST (pinned) crops: every step's H2D of the
-          crops + D2H of ids/distances inside the timed region, one batch in flight
+  e2e   : the same through RecognizerPipeline.recognize_stream() with HOST crops (numpy arrays): every step's packing
+          into pinned memory, H2D of the crops and D2H of ids/distances inside the timed region, one batch in flight
   roofline     : dominant kernel, timed live with CUDA events around every launch of a profiled pass
   cpu_baseline : the CPU oracle (torch fp32 restatement of the reference path) on a bounded sample
 
@@ -64,13 +64,24 @@ def parse():
     return ap.parse_args()
 
 
+QUICKFIT_VIT = ROOT / "tests" / "golden" / "quickfit_vit_small.npz"
+QUICKFIT_YOLO = ROOT / "tests" / "golden" / "quickfit_yolov5s.npz"
+
+
 def encoder_state(seed: int = 0):
-    """timm-style random init of ViT-S (no network for checkpoints); same on every rank."""
+    """ViT-S weights, the same on every rank and on both arms: the quick-fit checkpoint (tools/quickfit_recognizer.py; a
+    full-depth ViT-S fitted for ~3 minutes on the synthetic glyphs, fp16-rounded) when it is in the tree, so that the
+    parity block compares top-1 ids with real margins; timm-style random init otherwise (no network for checkpoints).
+    Throughput does not depend on the weight values (no data-dependent control flow on the path).
+    -> (state dict, description)."""
+    if QUICKFIT_VIT.exists() and os.environ.get("EFFOCR_BENCH_RANDOM_INIT") != "1":
+        sd = {k: torch.from_numpy(v.astype(np.float32)) for k, v in np.load(QUICKFIT_VIT).items()}
+        return sd, "quick-fit ViT-S (tests/golden/quickfit_vit_small.npz)"
     from effocr_b200.encoders import TimmViTParams
 
     torch.manual_seed(seed)
     net = TimmViTParams(MODEL)
-    return {"net." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    return {"net." + k: v.detach().clone() for k, v in net.state_dict().items()}, "random-init ViT-S (timm init)"
 
 
 # ------------------------------------------------------------------------------- clocks sampler
@@ -171,7 +182,7 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = encoder_state(0)
+    sd, _weights = encoder_state(0)
     sample = 64
     crops, _ = synth.synthetic_crops(sample, seed=0)
     g = torch.Generator().manual_seed(1)
@@ -186,7 +197,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)", "value": val,
         "unit": "crops/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        # a step of this arm is a bounded SAMPLE of the workload's batch (the CPU path needs ~16 s per 1024-crop batch):
+        # ms_per_step is scaled to the full batch so that both arms' ms_per_step describe the same unit of work
+        "ms_per_step": dt / args.steps * 1e3 * args.batch / sample, "ms_per_sample_step": dt / args.steps * 1e3,
+        "sample_crops_per_step": sample, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": val, "unit": "crops/s", "cores": cores, "kind": "port",
@@ -308,7 +322,7 @@ def main():
         pass
 
     B, K = args.batch, args.k
-    sd = encoder_state(0)
+    sd, weights_desc = encoder_state(0)
     D, mlp = 384, 1536
     crops, _labels = synth.synthetic_crops(B, seed=rank)
 
@@ -373,15 +387,23 @@ def main():
 
     # ---- end-to-end timing (host buffers in, host results out): the public streaming API keeps one batch in flight,
     # every step's H2D of the pinned crops and D2H of its ids / distances is inside the timed region
+    # host packing is part of the step: every step copies the numpy crops into a pinned staging buffer (taken from a
+    # small reusable pool), uploads it, and reads ids / distances back
+    pool = ops.PinnedPool()
+
+    def host_batches(n_steps):
+        for _ in range(n_steps):
+            yield PackedCrops(crops, pool=pool)
+
     for _ in range(2):
         step_e2e()
-    for res in pipe.recognize_stream((packed for _ in range(2)), K):
+    for res in pipe.recognize_stream(host_batches(3), K):
         pass
     barrier()
     t0 = time.perf_counter()
     e0.record()
     n_e2e = 0
-    for res in pipe.recognize_stream((packed for _ in range(args.steps)), K):
+    for res in pipe.recognize_stream(host_batches(args.steps), K):
         n_e2e += 1
     e1.record()
     barrier()
@@ -503,20 +525,25 @@ def main():
             s64 = emb_ref.double() @ iv.double().t()
             top2 = torch.topk(s64, 2, dim=1).values
             margin = top2[:, 0] - top2[:, 1]
-            decidable = margin > 4 * rel * 1.0
+            decidable = margin > 4 * max(rel, 1e-3)  # SURVEY.md 8c rule 3: 4 x the embedding tolerance
             agree = (idx_gpu[:, 0] == idx_ref[:, 0])
+            trained = weights_desc.startswith("quick-fit")
+            parity_ok = rel <= 1e-3 and (not trained or (float(decidable.float().mean()) >= 0.95 and bool(agree[decidable].all())))
             cpu_block = {"value": ncpu / dt, "unit": "crops/s", "cores": cores, "kind": "port",
                          "sample": f"first {ncpu} crops of the same batch, torch fp32 on {cores} host threads, "
                                    "oracle port (timm/faiss/onnxruntime are not installable here)",
                          "parity": {"max_rel_embedding_err": rel, "top1_agree": float(agree.float().mean()),
                                     "decidable_frac": float(decidable.float().mean()),
-                                    "top1_agree_decidable": float(agree[decidable].float().mean()) if decidable.any() else None}}
+                                    "top1_agree_decidable": float(agree[decidable].float().mean()) if decidable.any() else None,
+                                    "rule": "embeddings within 1e-3 relative; with trained weights >= 95 % of the sample decidable "
+                                            "(oracle top-1 / top-2 margin > 4e-3) and every decidable top-1 id identical",
+                                    "ok": bool(parity_ok)}}
 
         line = {
             "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)",
             "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "numerics": "f16 operands, f32 accumulate / residual stream / LayerNorm / softmax", "data": "synthetic (Pillow-rendered glyph crops, random-init ViT-S)",
+            "dtype": "f16", "numerics": "f16 operands, f32 accumulate / residual stream / LayerNorm / softmax", "data": f"synthetic (Pillow-rendered glyph crops; {weights_desc})",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": packed.h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -533,6 +560,8 @@ def main():
         if pipe_block is not None:
             line["pipeline_c3"] = pipe_block
         print(json.dumps(line), flush=True)
+        if cpu_block is not None and not cpu_block["parity"]["ok"]:
+            raise SystemExit(f"bench.py: parity against the CPU oracle FAILED: {cpu_block['parity']}")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -1,5 +1,7 @@
 #include "host_common.h"
 
+#include <stdlib.h>
+
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -20,7 +22,22 @@ int cuda_fail(cudaError_t e, const char* what) {
   return EFFOCR_ERR_CUDA;
 }
 
+static thread_local int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
 int sm_count() {
+  // EFFOCR_SM_LIMIT (experiments) / set_sm_limit (two half-batches on two streams, each on half of the SMs): persistent
+  // kernels size their grids from this value
+  static const int env_limit = [] {
+    const char* e = getenv("EFFOCR_SM_LIMIT");
+    return e ? atoi(e) : 0;
+  }();
+  const int lim = g_sm_limit > 0 ? g_sm_limit : env_limit;
+  const int n = sm_count_physical();
+  return (lim > 0 && lim < n) ? lim : n;
+}
+
+int sm_count_physical() {
   static int cached[64] = {0};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;

@@ -47,8 +47,11 @@ class KernelScope {
   cudaStream_t stream_;
 };
 
-// Number of SMs on the current device (148 on B200); cached per device.
+// Number of SMs persistent kernels may occupy: the device's SM count (148 on B200) unless a limit is in force.
 int sm_count();
+int sm_count_physical();
+// Per-host-thread cap on sm_count() (0 = none): lets two independent launch sequences share the device side by side.
+void set_sm_limit(int n);
 // Fails loudly unless the current device is compute capability 10.x.
 int require_sm100();
 

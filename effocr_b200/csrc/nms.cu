@@ -12,16 +12,20 @@
 
 namespace effocr {
 
-constexpr int kNmsMaxCand = 8192;  // per image; the reference's max_nms is 30000 (> 25200 predictions at 640^2)
+constexpr int kNmsSharedFlags = 8192;  // suppression flags live in shared memory up to this many candidates, else in HBM
+constexpr int kNmsMaxNms = 30000;      // the reference keeps the max_nms = 30000 best candidates (:198, :257)
 
 struct NmsCand {
   float x1, y1, x2, y2, conf, cls;
   int idx, pad;
 };
 
+// Every prediction that passes the confidence filter becomes a candidate: the per-image capacity `cap` is >= npred, so
+// nothing is ever dropped here (the reference never truncates before its sort either).  slot_of maps a prediction
+// index to its candidate slot so that the sort below can carry (confidence, prediction index) keys only.
 __global__ void __launch_bounds__(256) nms_filter_kernel(const float* __restrict__ pred, int B, int npred, int no,
-                                                         float conf_thres, NmsCand* __restrict__ cand,
-                                                         int* __restrict__ count) {
+                                                         float conf_thres, int cap, NmsCand* __restrict__ cand,
+                                                         int* __restrict__ slot_of, int* __restrict__ count) {
   const long long total = static_cast<long long>(B) * npred;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -37,8 +41,7 @@ __global__ void __launch_bounds__(256) nms_filter_kernel(const float* __restrict
       if (v > best) { best = v; bc = c - 5; }  // first maximum wins, like torch.max
     }
     if (!(best > conf_thres)) continue;
-    const int slot = atomicAdd(&count[b], 1);
-    if (slot >= kNmsMaxCand) continue;
+    const int slot = atomicAdd(&count[b], 1);  // slot < npred <= cap: every survivor has a slot
     NmsCand c;
     const float hw = __fmul_rn(p[2], 0.5f), hh = __fmul_rn(p[3], 0.5f);  // x / 2 is exact in fp32
     c.x1 = __fsub_rn(p[0], hw);
@@ -49,36 +52,35 @@ __global__ void __launch_bounds__(256) nms_filter_kernel(const float* __restrict
     c.cls = static_cast<float>(bc);
     c.idx = k;
     c.pad = 0;
-    cand[static_cast<long long>(b) * kNmsMaxCand + slot] = c;
+    cand[static_cast<long long>(b) * cap + slot] = c;
+    slot_of[i] = slot;
   }
 }
 
 // One CTA per image: bitonic sort of the candidate keys (global scratch), then greedy suppression.
 __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsCand* __restrict__ cand_all,
                                                           const int* __restrict__ count_all,
-                                                          unsigned long long* __restrict__ keys_all, float iou_thres,
+                                                          const int* __restrict__ slot_of_all, int npred, int cap,
+                                                          unsigned long long* __restrict__ keys_all,
+                                                          unsigned char* __restrict__ removed_all, float iou_thres,
                                                           float max_wh, int max_det, float* __restrict__ out,
                                                           int* __restrict__ out_count) {
-  __shared__ unsigned char removed[kNmsMaxCand];
-  __shared__ int s_kept;
+  __shared__ unsigned char s_removed[kNmsSharedFlags];
   const int b = blockIdx.x;
-  const NmsCand* cand = cand_all + static_cast<long long>(b) * kNmsMaxCand;
-  unsigned long long* keys = keys_all + static_cast<long long>(b) * kNmsMaxCand;
+  const NmsCand* cand = cand_all + static_cast<long long>(b) * cap;
+  const int* slot_of = slot_of_all + static_cast<long long>(b) * npred;
+  unsigned long long* keys = keys_all + static_cast<long long>(b) * cap;
   int n = count_all[b];
-  if (n > kNmsMaxCand) n = kNmsMaxCand;
   int np2 = 1;
-  while (np2 < n) np2 <<= 1;
-  // key = conf bits (positive floats order like unsigned ints) : ~prediction index : slot
+  while (np2 < n) np2 <<= 1;  // <= cap (a power of two >= npred >= n)
+  // key = confidence bits (positive floats order like unsigned ints) : inverted prediction index (ties: lower index first)
   for (int i = threadIdx.x; i < np2; i += blockDim.x) {
     unsigned long long k = 0ull;
     if (i < n) {
       const unsigned int cb = __float_as_uint(cand[i].conf);
-      // 32 bits conf | 16 bits... use two-word composite: high = conf, mid = inverted prediction index (15 bits enough
-      // for 25200 < 32768 is NOT general) -> keep full 32-bit inverted index and carry the slot in a parallel pass below
       k = (static_cast<unsigned long long>(cb) << 32) | static_cast<unsigned long long>(0xFFFFFFFFu - static_cast<unsigned int>(cand[i].idx));
     }
     keys[i] = k;
-    if (i < kNmsMaxCand) removed[i] = 0;
   }
   __syncthreads();
   // descending bitonic sort
@@ -95,23 +97,20 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsCand* __restr
       __syncthreads();
     }
   }
-  // The key carries the prediction index, not the slot: recover the slot of sorted position r by a second
-  // table (prediction index -> slot is not dense), so store slots in place of keys: one linear probe pass.
-  // n is small (tens to a few thousand): each thread resolves its positions by scanning the candidates.
+  if (n > kNmsMaxNms) n = kNmsMaxNms;  // x[argsort(conf, descending)[:max_nms]]
+  unsigned char* removed = n <= kNmsSharedFlags ? s_removed : removed_all + static_cast<long long>(b) * cap;
+  // sorted position -> candidate slot (through the prediction index the key carries)
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    const unsigned int want = 0xFFFFFFFFu - static_cast<unsigned int>(keys[r] & 0xFFFFFFFFull);
-    int slot = 0;
-    for (int s = 0; s < n; ++s)
-      if (static_cast<unsigned int>(cand[s].idx) == want) { slot = s; break; }
-    keys[r] = static_cast<unsigned long long>(slot);
+    const unsigned int idx = 0xFFFFFFFFu - static_cast<unsigned int>(keys[r] & 0xFFFFFFFFull);
+    keys[r] = static_cast<unsigned long long>(slot_of[idx]);
+    removed[r] = 0;
   }
-  if (threadIdx.x == 0) s_kept = 0;
   __syncthreads();
-  // greedy suppression in sorted order
-  for (int i = 0; i < n; ++i) {
-    if (removed[i]) continue;  // uniform: written before the last barrier
-    const int kept = s_kept;
-    if (kept >= max_det) break;
+  // greedy suppression in sorted order; `kept` advances identically in every thread (removed[i] was written before
+  // the barrier that ended the previous kept iteration), so no shared counter is read while another thread writes it
+  int kept = 0;
+  for (int i = 0; i < n && kept < max_det; ++i) {
+    if (removed[i]) continue;
     const NmsCand ci = cand[keys[i]];
     const float off_i = __fmul_rn(ci.cls, max_wh);
     const float ix1 = __fadd_rn(ci.x1, off_i), iy1 = __fadd_rn(ci.y1, off_i), ix2 = __fadd_rn(ci.x2, off_i),
@@ -133,18 +132,21 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(const NmsCand* __restr
     if (threadIdx.x == 0) {
       float* o = out + (static_cast<long long>(b) * max_det + kept) * 6;
       o[0] = ci.x1; o[1] = ci.y1; o[2] = ci.x2; o[3] = ci.y2; o[4] = ci.conf; o[5] = ci.cls;
-      s_kept = kept + 1;
     }
+    ++kept;
     __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) out_count[b] = s_kept;
+  if (threadIdx.x == 0) out_count[b] = kept;
 }
 
 struct NmsWorkspace {
   NmsCand* cand = nullptr;
   unsigned long long* keys = nullptr;
+  unsigned char* removed = nullptr;
+  int* slot_of = nullptr;
   int* count = nullptr;
+  size_t cap_cand = 0;  // batch * cap elements
+  size_t cap_pred = 0;  // batch * npred elements
   int cap_images = 0;
 };
 static thread_local NmsWorkspace g_ws;  // one per calling host thread (the shim's worker threads)
@@ -163,13 +165,18 @@ extern "C" int effocr_nms(const float* d_pred, int batch, int npred, int no, flo
   if (!d_pred || !d_out || !d_count) return fail(EFFOCR_ERR_INVALID, "nms: null buffer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   NmsWorkspace& ws = g_ws;
-  if (batch > ws.cap_images) {
-    cudaFree(ws.cand); cudaFree(ws.keys); cudaFree(ws.count);
+  int cap = 1;
+  while (cap < npred) cap <<= 1;  // per-image candidate capacity: every prediction can be a candidate (no silent truncation)
+  const size_t need_cand = static_cast<size_t>(batch) * cap, need_pred = static_cast<size_t>(batch) * (npred > 0 ? npred : 1);
+  if (need_cand > ws.cap_cand || need_pred > ws.cap_pred || batch > ws.cap_images) {
+    cudaFree(ws.cand); cudaFree(ws.keys); cudaFree(ws.removed); cudaFree(ws.slot_of); cudaFree(ws.count);
     ws = NmsWorkspace();
-    EFFOCR_CUDA(cudaMalloc(&ws.cand, sizeof(NmsCand) * kNmsMaxCand * static_cast<size_t>(batch)));
-    EFFOCR_CUDA(cudaMalloc(&ws.keys, sizeof(unsigned long long) * kNmsMaxCand * static_cast<size_t>(batch)));
+    EFFOCR_CUDA(cudaMalloc(&ws.cand, sizeof(NmsCand) * need_cand));
+    EFFOCR_CUDA(cudaMalloc(&ws.keys, sizeof(unsigned long long) * need_cand));
+    EFFOCR_CUDA(cudaMalloc(&ws.removed, need_cand));
+    EFFOCR_CUDA(cudaMalloc(&ws.slot_of, sizeof(int) * need_pred));
     EFFOCR_CUDA(cudaMalloc(&ws.count, sizeof(int) * static_cast<size_t>(batch)));
-    ws.cap_images = batch;
+    ws.cap_cand = need_cand; ws.cap_pred = need_pred; ws.cap_images = batch;
   }
   EFFOCR_CUDA(cudaMemsetAsync(ws.count, 0, sizeof(int) * batch, s));
   if (npred > 0) {
@@ -178,12 +185,13 @@ extern "C" int effocr_nms(const float* d_pred, int batch, int npred, int no, flo
     if (g > 148 * 16) g = 148 * 16;
     {
       KernelScope ks(PROF_NMS, s);
-      nms_filter_kernel<<<static_cast<int>(g), 256, 0, s>>>(d_pred, batch, npred, no, conf_thres, ws.cand, ws.count);
+      nms_filter_kernel<<<static_cast<int>(g), 256, 0, s>>>(d_pred, batch, npred, no, conf_thres, cap, ws.cand, ws.slot_of, ws.count);
     }
   }
   {
     KernelScope ks(PROF_NMS, s);
-    nms_select_kernel<<<batch, 1024, 0, s>>>(ws.cand, ws.count, ws.keys, iou_thres, 7680.0f, max_det, d_out, d_count);
+    nms_select_kernel<<<batch, 1024, 0, s>>>(ws.cand, ws.count, ws.slot_of, npred, cap, ws.keys, ws.removed, iou_thres, 7680.0f,
+                                              max_det, d_out, d_count);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

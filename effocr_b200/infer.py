@@ -71,7 +71,20 @@ class EffOCRPipeline:
     """localizer (EffLocalizer) + recognizer (RecognizerPipeline) + candidate chars."""
 
     def __init__(self, localizer: EffLocalizer, recognizer: RecognizerPipeline, candidate_chars, lang: str = "en",
-                 vertical: bool = False, knn: int = 1, anchor_margin=None, blacklist=None):
+                 vertical: bool = False, knn: int = 1, anchor_margin=None, blacklist=None, box_convention: str = "onnx",
+                 score_thresh: float = 0.5, score_thresh_word: float = 0.5):
+        """box_convention: which of the reference's two drivers the host stage between the GPU phases follows.
+        "onnx"  -- infer_effocr_onnx_multi.py:256-322: letterbox-pixel boxes, no score filter after NMS, crop columns
+                   rescaled by (width / 640), heights / bottoms in letterbox pixels;
+        "torch" -- infer_effocr.py:261-302 behind the mmdet.apis shim (effocr_b200/mmdet_shim.py): boxes mapped back to
+                   ORIGINAL image pixels, `score > score_thresh` / `score_thresh_word` applied by the caller (:350-352),
+                   all four coordinates int(round(.)) and double-clipped; the localizer should then be built with the
+                   shim's low confidence floor (mmdet_shim.DEFAULT_CONF_FLOOR)."""
+        if box_convention not in ("onnx", "torch"):
+            raise ValueError("box_convention must be 'onnx' or 'torch'")
+        self.box_convention = box_convention
+        self.score_thresh = score_thresh
+        self.score_thresh_word = score_thresh_word
         self.localizer = localizer
         self.recognizer = recognizer
         self.candidate_chars = list(candidate_chars)
@@ -105,6 +118,8 @@ class EffOCRPipeline:
         # numpy float32 rows: the same float32 arithmetic / comparisons as the reference's torch rows, without a
         # ~5 us torch dispatch per scalar operation (the O(n w) word-end search is ~500 scalar ops per line)
         result = np.asarray(result, dtype=np.float32)
+        if self.box_convention == "torch":
+            return self._boxes_for_line_torch(result, im_h, im_w)
         bboxes, labels = result[:, :4], result[:, -1]
         word_end_idx = []
         if self.lang == "en":
@@ -117,6 +132,25 @@ class EffOCRPipeline:
                 char_b = char_b[np.argsort(char_b[:, 1 if self.vertical else 0], kind="stable")]
         rects = crop_rects_onnx_path(char_b, im_h, im_w, self.vertical)
         heights = list(char_b[:, 3] - char_b[:, 1])  # float32 scalars, as b[3] - b[1] row by row
+        bottoms = list(char_b[:, 3])
+        return list(char_b), word_end_idx, rects, heights, bottoms
+
+    def _boxes_for_line_torch(self, result, im_h, im_w):
+        """infer_effocr.py:270-302 on the shim's un-letterboxed detections (see __init__)."""
+        from .mmdet_shim import unletterbox
+
+        det = unletterbox(result, im_h, im_w, self.localizer._input_shape)
+        labels, score = det[:, 5], det[:, 4]
+        char_b = det[(labels == 0) & (score > np.float32(self.score_thresh))][:, :4]
+        word_end_idx = []
+        if self.lang == "en":
+            word_b = det[(labels == 1) & (score > np.float32(self.score_thresh_word))][:, :4]
+            if len(char_b) != 0:  # filtering commutes with the reference's stable sort
+                char_b, word_end_idx = textproc.en_preprocess_np(char_b, word_b, vertical=self.vertical)
+        elif len(char_b) != 0:
+            char_b = char_b[np.argsort(char_b[:, 1 if self.vertical else 0], kind="stable")]
+        rects = [crop_rect_torch_path(b, im_h, im_w, self.vertical) for b in char_b]
+        heights = list(char_b[:, 3] - char_b[:, 1])
         bottoms = list(char_b[:, 3])
         return list(char_b), word_end_idx, rects, heights, bottoms
 
@@ -133,7 +167,7 @@ class EffOCRPipeline:
         for li, (im, det) in enumerate(zip(images_rgb, dets)):
             h, w = im.shape[:2]
             char_b, wei, rects, heights, bottoms = self._boxes_for_line(det, h, w)
-            per_line.append((char_b, wei, heights, bottoms, len(rects)))
+            per_line.append((char_b, wei, heights, bottoms, rects))
             all_rects += [(li,) + r for r in rects]
         boxes, n = ops.pack_boxes(all_rects) if all_rects else (None, 0)
         done = torch.cuda.current_stream().record_event()
@@ -154,9 +188,10 @@ class EffOCRPipeline:
         if idx is not None:
             idx = idx.cpu().numpy()
         pos = 0
-        for (char_b, wei, heights, bottoms, n) in st["per_line"]:
+        for (char_b, wei, heights, bottoms, rects) in st["per_line"]:
+            n = len(rects)
             if n == 0:
-                results.append({"text": None, "nns": [], "char_boxes": [], "word_end_idx": []})
+                results.append({"text": None, "nns": [], "char_boxes": [], "word_end_idx": [], "rects": []})
                 continue
             rows = idx[pos:pos + n]
             pos += n
@@ -167,7 +202,8 @@ class EffOCRPipeline:
                 # the ONNX driver passes the un-stripped first-NN string's characters; lengths must agree (:94)
                 first = [x[0] for x in nearest]
                 text = textproc.en_postprocess(first, wei, heights, bottoms, anchor_margin=self.anchor_margin)
-            results.append({"text": text, "nns": nns, "char_boxes": [b.tolist() for b in char_b], "word_end_idx": wei})
+            results.append({"text": text, "nns": nns, "char_boxes": [b.tolist() for b in char_b], "word_end_idx": wei,
+                            "rects": rects})
         return results
 
     def stage_recognize(self, st):

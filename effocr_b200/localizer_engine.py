@@ -8,7 +8,8 @@ letterbox pixels; confidence-sorted) per image, and the static helpers `letterbo
 csrc/yolo.cu / csrc/nms.cu on the B200 instead of onnxruntime + torchvision on the CPU.
 
 `model_path`: an ultralytics-keyed YOLOv5s state dict (`model.{i}...`; what `best.pt['model'].state_dict()` holds),
-as a dict or a .pth/.pt/.npz path.  ONNX graphs are not parsed.  Only model_backend='yolo' is implemented
+as a dict, a .pth/.pt/.npz path, an ultralytics `best.pt` pickle, or the exported `.onnx` (its initializers are read,
+the graph is not executed: effocr_b200/weights_io.py).  Only model_backend='yolo' is implemented
 (mmdetection / detectron2 back-ends are out of scope).
 """
 from __future__ import annotations
@@ -44,20 +45,9 @@ def yolo_weight_order():
 
 
 def _load_state(model):
-    if isinstance(model, dict):
-        sd = model
-    else:
-        path = str(model)
-        if path.endswith(".onnx"):
-            raise _lib.EffocrError("EffLocalizer: pass the YOLOv5s weights as an ultralytics-keyed state dict (.pth); "
-                                   "ONNX graphs are not parsed by effocr_b200")
-        if path.endswith(".npz"):
-            sd = {k: torch.from_numpy(v) for k, v in np.load(path).items()}
-        else:
-            sd = torch.load(path, map_location="cpu", weights_only=False)
-            if isinstance(sd, dict) and "model" in sd and hasattr(sd["model"], "state_dict"):
-                sd = sd["model"].float().state_dict()  # ultralytics best.pt
-    return sd
+    from .weights_io import load_yolo_state
+
+    return load_yolo_state(model)
 
 
 LETTERBOX_PLAN_DTYPE = np.dtype([("new_width", "<i4"), ("new_height", "<i4"), ("left", "<i4"), ("top", "<i4"),
@@ -182,6 +172,8 @@ class EffLocalizer:
                  input_shape=(640, 640), model_backend="yolo", max_batch=16):
         if model_backend != "yolo":
             raise NotImplementedError("Backend {} is not implemented".format(model_backend))
+        if input_shape is None:  # the reference falls back to the model's own (static) shape, localizer_engine.py:38-41
+            input_shape = (640, 640)
         self._eng_net = YoloEngine(_load_state(model_path), max_batch=max_batch, max_shape=tuple(input_shape))
         self._iou_thresh = iou_thresh
         self._conf_thresh = conf_thresh
@@ -235,56 +227,60 @@ class EffLocalizer:
 
     @staticmethod
     def preprocess_bgr(im0, input_shape):
-        im = EffLocalizer.letterbox(im0, input_shape, stride=32, auto=False)[0]
-        im = im.transpose((2, 0, 1))[::-1]  # HWC to CHW, BGR to RGB
-        im = np.ascontiguousarray(im).astype(np.float32) / 255.0
-        if im.ndim == 3:
-            im = np.expand_dims(im, 0)
-        return im
+        """BGR u8 [H, W, 3] -> the model input f32 [1, 3, H', W'] (RGB, 0..1), letterboxed (localizer_engine.py:79-85)."""
+        boxed = EffLocalizer.letterbox(im0, input_shape, stride=32, auto=False)[0]
+        chw_rgb = np.ascontiguousarray(boxed[:, :, ::-1].transpose(2, 0, 1))
+        return (chw_rgb.astype(np.float32) / 255.0)[None] if chw_rgb.ndim == 3 else chw_rgb.astype(np.float32) / 255.0
 
     @staticmethod
     def letterbox(im, new_shape=(640, 640), color=(114, 114, 114), auto=True, scaleFill=False, scaleup=True, stride=32):
-        """localizer_engine.py:107-138 (ultralytics letterbox): resize keeping aspect, pad to new_shape."""
+        """localizer_engine.py:107-138 (the ultralytics letterbox): aspect-preserving resize + constant border.
+        -> (image, (ratio_w, ratio_h), (dw, dh)).  The default path (auto=False, scaleFill=False, scaleup=True) goes
+        through `letterbox_geometry`, the same arithmetic the device letterbox kernel's plan uses."""
         import cv2
 
-        shape = im.shape[:2]
+        h, w = im.shape[:2]
         if isinstance(new_shape, int):
             new_shape = (new_shape, new_shape)
-        r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+        gain = min(new_shape[0] / h, new_shape[1] / w)
         if not scaleup:
-            r = min(r, 1.0)
-        ratio = r, r
-        new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
-        dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
-        if auto:
-            dw, dh = np.mod(dw, stride), np.mod(dh, stride)
-        elif scaleFill:
-            dw, dh = 0.0, 0.0
-            new_unpad = (new_shape[1], new_shape[0])
-            ratio = new_shape[1] / shape[1], new_shape[0] / shape[0]
-        dw /= 2
-        dh /= 2
-        if shape[::-1] != new_unpad:
-            im = cv2.resize(im, new_unpad, interpolation=cv2.INTER_LINEAR)
-        top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
-        left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
-        im = cv2.copyMakeBorder(im, top, bottom, left, right, cv2.BORDER_CONSTANT, value=color)
-        return im, ratio, (dw, dh)
+            gain = min(gain, 1.0)
+        ratio = (gain, gain)
+        if scaleFill and not auto:
+            out_w, out_h, pad_w, pad_h = new_shape[1], new_shape[0], 0.0, 0.0
+            ratio = (new_shape[1] / w, new_shape[0] / h)
+        else:
+            out_w, out_h = int(round(w * gain)), int(round(h * gain))
+            pad_w, pad_h = new_shape[1] - out_w, new_shape[0] - out_h
+            if auto:  # minimum rectangle: pad only up to the next stride multiple
+                pad_w, pad_h = np.mod(pad_w, stride), np.mod(pad_h, stride)
+        pad_w, pad_h = pad_w / 2, pad_h / 2
+        if (w, h) != (out_w, out_h):
+            im = cv2.resize(im, (out_w, out_h), interpolation=cv2.INTER_LINEAR)
+        edges = [int(round(v)) for v in (pad_h - 0.1, pad_h + 0.1, pad_w - 0.1, pad_w + 0.1)]  # top, bottom, left, right
+        if not auto and not scaleFill and scaleup:
+            assert (out_w, out_h, edges[2], edges[0]) == letterbox_geometry(h, w, new_shape)
+        im = cv2.copyMakeBorder(im, *edges, cv2.BORDER_CONSTANT, value=color)
+        return im, ratio, (pad_w, pad_h)
 
     @staticmethod
     def xywh2xyxy(x):
+        """[n, 4+] centre/size boxes -> corner boxes (localizer_engine.py:140-148); other columns are kept."""
         y = x.clone() if isinstance(x, torch.Tensor) else np.copy(x)
-        y[:, 0] = x[:, 0] - x[:, 2] / 2
-        y[:, 1] = x[:, 1] - x[:, 3] / 2
-        y[:, 2] = x[:, 0] + x[:, 2] / 2
-        y[:, 3] = x[:, 1] + x[:, 3] / 2
+        half_w, half_h = x[:, 2] / 2, x[:, 3] / 2
+        y[:, 0], y[:, 2] = x[:, 0] - half_w, x[:, 0] + half_w
+        y[:, 1], y[:, 3] = x[:, 1] - half_h, x[:, 1] + half_h
         return y
 
     @staticmethod
     def box_iou(box1, box2, eps=1e-7):
-        (a1, a2), (b1, b2) = box1.unsqueeze(1).chunk(2, 2), box2.unsqueeze(0).chunk(2, 2)
-        inter = (torch.min(a2, b2) - torch.max(a1, b1)).clamp(0).prod(2)
-        return inter / ((a2 - a1).prod(2) + (b2 - b1).prod(2) - inter + eps)
+        """Pairwise IoU of corner boxes [n, 4] x [m, 4] -> [n, m] (localizer_engine.py:150-169)."""
+        lo = torch.max(box1[:, None, :2], box2[None, :, :2])
+        hi = torch.min(box1[:, None, 2:4], box2[None, :, 2:4])
+        inter = (hi - lo).clamp(min=0).prod(dim=2)
+        area1 = (box1[:, 2:4] - box1[:, :2]).prod(dim=1)
+        area2 = (box2[:, 2:4] - box2[:, :2]).prod(dim=1)
+        return inter / (area1[:, None] + area2[None, :] - inter + eps)
 
     @staticmethod
     def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,

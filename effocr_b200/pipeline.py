@@ -17,7 +17,9 @@ from .engine import ConvNextEngine, FlatIPIndex, VitEngine, make_encoder_engine
 class PackedCrops:
     """Pinned host staging for one batch: pixels + image descriptors + crop boxes."""
 
-    def __init__(self, arrays, boxes=None):
+    def __init__(self, arrays, boxes=None, pool: "ops.PinnedPool | None" = None):
+        """`pool`: take the pixel staging buffer from a PinnedPool instead of page-locking a fresh one (a per-batch
+        cudaHostAlloc costs milliseconds); the buffer returns to the pool once `to_device()`'s copy has completed."""
         descs = np.zeros(len(arrays), dtype=ops.IMAGE_DESC_DTYPE)
         off = 0
         for i, a in enumerate(arrays):
@@ -25,7 +27,12 @@ class PackedCrops:
             descs[i] = (off, h, w, w * 3, 0)
             off += (h * w * 3 + 255) // 256 * 256
         pin = torch.cuda.is_available()
-        self.pixels = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=pin)
+        self._pool_entry = None
+        if pool is not None and pin:
+            self._pool_entry = pool.get(max(off, 1))
+            self.pixels = self._pool_entry[0][:max(off, 1)]
+        else:
+            self.pixels = torch.empty(max(off, 1), dtype=torch.uint8, pin_memory=pin)
         hv = self.pixels.numpy()
         for i, a in enumerate(arrays):
             o = int(descs[i]["offset"])
@@ -48,8 +55,11 @@ class PackedCrops:
         return self.pixels.numel() + self.images.numel() + self.boxes.numel()
 
     def to_device(self):
-        return (self.pixels.cuda(non_blocking=True), self.images.cuda(non_blocking=True),
-                self.boxes.cuda(non_blocking=True), self.n)
+        out = (self.pixels.cuda(non_blocking=True), self.images.cuda(non_blocking=True),
+               self.boxes.cuda(non_blocking=True), self.n)
+        if self._pool_entry is not None:
+            self._pool_entry[1] = torch.cuda.current_stream().record_event()
+        return out
 
 
 class RecognizerPipeline:

@@ -7,8 +7,9 @@ B200 instead of an onnxruntime CPU session.  `run` may be called concurrently fr
 on one object (infer_effocr_onnx_multi.py:357-364): calls are serialised on the handle's workspace.
 
 `model` is the recognizer checkpoint: a timm-keyed state dict (`net.*`, what the reference's
-training script saves as enc_best.pth) given as a path or a dict.  ONNX graphs are not parsed (the
-`onnx` package is not part of this stack); export the same weights as .pth instead.
+training script saves as enc_best.pth) given as a path or a dict, or its ONNX export `enc_best.onnx`
+(scripts/recognizer_onnx_export.py) -- the initializers are read back into the state dict, the graph itself is
+not executed (effocr_b200/weights_io.py).
 """
 from __future__ import annotations
 
@@ -20,15 +21,9 @@ from .engine import VitEngine
 
 
 def _load_state(model):
-    if isinstance(model, dict):
-        return model
-    path = str(model)
-    if path.endswith(".onnx"):
-        raise _lib.EffocrError("EffRecognizer: pass the encoder weights as a timm-keyed .pth state dict (enc_best.pth); "
-                               "ONNX graphs are not parsed by effocr_b200")
-    if path.endswith(".npz"):
-        return {k: torch.from_numpy(v) for k, v in np.load(path).items()}
-    return torch.load(path, map_location="cpu")
+    from .weights_io import load_encoder_state
+
+    return load_encoder_state(model)
 
 
 class EffRecognizer:

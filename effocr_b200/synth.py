@@ -16,8 +16,10 @@ def _font(size: int):
     return ImageFont.load_default(size=size)
 
 
-def render_line(text: str, height: int = 64, width: int = 1024, font_size: int = 40, x0: int = 6):
-    """-> (u8 [height, width, 3] RGB, char_boxes [n,4] float32 xyxy, word_boxes [m,4], chars list)."""
+def render_line(text: str, height: int = 64, width: int = 1024, font_size: int = 40, x0: int = 6, tracking: float = 0.0):
+    """-> (u8 [height, width, 3] RGB, char_boxes [n,4] float32 xyxy, word_boxes [m,4], chars list).
+    `tracking`: extra pixels between consecutive glyphs (letter-spacing).  The reference's localizer runs its NMS at
+    IoU 0.01 (infer_effocr_onnx_multi.py:441), which only keeps neighbouring characters whose boxes do not touch."""
     from PIL import Image, ImageDraw
 
     font = _font(font_size)
@@ -42,7 +44,7 @@ def render_line(text: str, height: int = 64, width: int = 1024, font_size: int =
         chars.append(ch)
         if word_start is None:
             word_start = float(l)
-        x += adv
+        x += adv + tracking
     if word_start is not None:
         word_boxes.append([word_start, 0.0, x, float(height)])
     return (np.asarray(img, dtype=np.uint8).copy(), np.asarray(char_boxes, dtype=np.float32).reshape(-1, 4),
@@ -58,13 +60,13 @@ def random_text(rng: np.random.Generator, n_glyphs: int) -> str:
     return " ".join(words)
 
 
-def synthetic_lines(n: int, seed: int = 0, height: int = 64, width: int = 1024):
+def synthetic_lines(n: int, seed: int = 0, height: int = 64, width: int = 1024, tracking: float = 0.0):
     """n rendered lines, 20-40 glyphs each (fewer if the line fills up)."""
     rng = np.random.default_rng(seed)
     out = []
     for _ in range(n):
         text = random_text(rng, int(rng.integers(20, 41)))
-        out.append(render_line(text, height, width, font_size=int(rng.integers(34, 44))))
+        out.append(render_line(text, height, width, font_size=int(rng.integers(34, 44)), tracking=tracking))
     return out
 
 

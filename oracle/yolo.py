@@ -149,7 +149,7 @@ def yolov5s_forward(sd, x: torch.Tensor, dtype=torch.float32, return_raw: bool =
         bs, _, ny, nx = t.shape
         t = t.view(bs, 3, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         raw.append(t)
-        yv, xv = torch.meshgrid(torch.arange(ny, dtype=dtype), torch.arange(nx, dtype=dtype), indexing="ij")
+        yv, xv = torch.meshgrid(torch.arange(ny, dtype=dtype, device=t.device), torch.arange(nx, dtype=dtype, device=t.device), indexing="ij")
         grid = torch.stack((xv, yv), 2).expand(1, 3, ny, nx, 2) - 0.5
         anchor = (sd["model.24.anchors"][l].to(dtype) * stride).view(1, 3, 1, 1, 2).expand(1, 3, ny, nx, 2)
         y = t.sigmoid()

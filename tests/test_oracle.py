@@ -259,3 +259,28 @@ def test_vectorised_crop_rects_equal_scalar_reference_semantics():
             assert infer.crop_rects_onnx_path(list(b), h, w, vertical) == exp
             assert all(type(v) is int for r in infer.crop_rects_onnx_path(b, h, w, vertical) for v in r)
     assert infer.crop_rects_onnx_path(np.zeros((0, 4), np.float32), 64, 1024, False) == []
+
+
+@pytest.mark.parametrize("convention,key", [("onnx", "infer_effocr_onnx_multi"), ("torch", "infer_effocr")])
+def test_oracle_pipeline_matches_reference_driver_golden(convention, key):
+    """oracle/pipeline.py (the whole hot path restated) reproduces, string for string, what the UNMODIFIED reference
+    drivers wrote for the same job when run over oracle back-ends (tests/golden/driver_golden.json, generated by
+    oracle/make_driver_golden.py): the orchestration restatement -- box ordering, word ends, crop rectangles, zero-padded
+    batches, decode, en_postprocess -- is pinned by the reference's own scripts."""
+    import json
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import driver_fixture as DF
+    from effocr_b200 import synth
+    from oracle import pipeline as OP
+    if not (DF.available() and DF.DRIVER_GOLDEN.exists()):
+        pytest.skip("quick-fit weights / driver golden not generated")
+    golden = json.loads(DF.DRIVER_GOLDEN.read_text())
+    n = 8  # a third of the job keeps the CPU suite short; the GPU tests cover all 24 lines
+    lines = [l[0] for l in synth.synthetic_lines(DF.N_LINES, seed=DF.SEED, tracking=DF.TRACKING)][:n]
+    vsd, ysd = DF.load_npz_state(DF.VIT_WEIGHTS), DF.load_npz_state(DF.YOLO_WEIGHTS)
+    xb = torch.from_numpy(np.load(DF.INDEX_VECTORS))
+    conf, k = (0.35, 1) if convention == "onnx" else (0.05, 10)
+    res = OP.run(lines, ysd, vsd, xb, synth.ASCII_GLYPHS, conf_thres=conf, iou_thres=0.01, convention=convention, k=k)
+    for i, r in enumerate(res):
+        assert r["text"] == golden[key].get(f"line_{i:03d}.png"), (i, r["text"], golden[key].get(f"line_{i:03d}.png"))
