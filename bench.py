@@ -57,8 +57,11 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline-lines", type=int, default=512,
+    ap.add_argument("--pipeline-lines", type=int, default=1000,
                     help="lines per GPU for the auxiliary whole-pipeline (config C3) measurement; 0 = skip")
+    ap.add_argument("--paths-lines", type=int, default=2048,
+                    help="line FILES per GPU for the path-driver measurement (config C5's mechanism: PNGs on disk -> "
+                         "lineio.run_effocr_paths_sharded); 0 = skip")
     ap.add_argument("--index-random", action="store_true",
                     help="profiling runs: random unit-norm prototypes instead of embedding rendered glyphs")
     return ap.parse_args()
@@ -240,37 +243,51 @@ def kernel_work(tag: str, B: int, D: int, mlp: int, n_index: int):
     return None, 0.0
 
 
-def time_pipeline_c3(args, rec_pipe, rank, barrier):
-    """localize (device letterbox -> YOLOv5s -> NMS) -> host box ordering -> crop -> ViT-S -> kNN(k=1) -> decode."""
+YOLO_FLOPS_PER_LINE_640 = 15_762_636_800  # YOLOv5s, nc = 2, 640 x 640 letterbox (matmul/conv FLOPs)
+
+
+def time_pipeline_c3(args, rec_pipe, rank, world, barrier, index_vectors):
+    """BASELINE config C3: localize (device letterbox -> YOLOv5s -> NMS) -> host box ordering -> crop -> ViT-S -> kNN (k = 1)
+    -> decode, host u8 lines in / strings out, `--pipeline-lines` (1000) lines per GPU in batches of 64."""
     from effocr_b200 import ops, synth
     from effocr_b200.infer import EffOCRPipeline, run_effocr
     from effocr_b200.localizer_engine import EffLocalizer, nms_device
 
     L, bl = args.pipeline_lines, 64
-    lines = [l[0] for l in synth.synthetic_lines(L, seed=1000 + rank)]
-    ysd = synth.background_suppressed_yolo_state(nc=2, seed=0)  # random-init detector that ignores the grey padding
-    loc = EffLocalizer(ysd, iou_thresh=0.01, conf_thresh=0.35, input_shape=(640, 640), max_batch=bl)
-    # random-init detector: set the confidence threshold at the quantile that leaves ~32 character boxes per line (SURVEY 8d)
-    chunk = lines[:bl]
-    px, im, _ = ops.pack_images(chunk)
-    pred = loc._eng_net.forward(ops.letterbox_resize(px, im, [c.shape[:2] for c in chunk], 640, 640))
-    lo, hi = 0.001, 0.999
-    for _ in range(18):
-        mid = 0.5 * (lo + hi)
-        o, c = nms_device(pred, mid, 0.01)
-        live = torch.arange(o.shape[1], device=o.device)[None, :] < c[:, None]
-        if float(((o[:, :, 5] == 0) & live).sum()) / len(chunk) > 32:  # class 0 = character boxes
-            lo = mid
-        else:
-            hi = mid
-    loc._conf_thresh = hi
+    lib = __import__("effocr_b200._lib", fromlist=["load"]).load()
+    trained = QUICKFIT_YOLO.exists() and os.environ.get("EFFOCR_BENCH_RANDOM_INIT") != "1"
+    tracking = 4.0 if trained else 0.0  # the quick-fit detector was fitted on letter-spaced lines (NMS runs at IoU 0.01)
+    lines = [l[0] for l in synth.synthetic_lines(L, seed=1000 + rank, tracking=tracking)]
+    precision = os.environ.get("EFFOCR_YOLO_PRECISION", "split")
+    if trained:
+        ysd = {k: torch.from_numpy(v.astype(np.float32)) for k, v in np.load(QUICKFIT_YOLO).items()}
+        loc = EffLocalizer(ysd, iou_thresh=0.01, conf_thresh=0.35, input_shape=(640, 640), max_batch=bl, precision=precision)
+        conf, weights = 0.35, "quick-fit YOLOv5s (tests/golden/quickfit_yolov5s.npz), reference thresholds conf 0.35 / iou 0.01"
+    else:
+        ysd = synth.background_suppressed_yolo_state(nc=2, seed=0)  # random-init detector that ignores the grey padding
+        loc = EffLocalizer(ysd, iou_thresh=0.01, conf_thresh=0.35, input_shape=(640, 640), max_batch=bl, precision=precision)
+        # random-init detector: confidence threshold at the quantile that leaves ~32 character boxes per line (SURVEY 8d)
+        chunk = lines[:bl]
+        px, im, _ = ops.pack_images(chunk)
+        pred = loc._eng_net.forward(ops.letterbox_resize(px, im, [c.shape[:2] for c in chunk], 640, 640))
+        lo, hi = 0.001, 0.999
+        for _ in range(18):
+            mid = 0.5 * (lo + hi)
+            o, c = nms_device(pred, mid, 0.01)
+            live = torch.arange(o.shape[1], device=o.device)[None, :] < c[:, None]
+            if float(((o[:, :, 5] == 0) & live).sum()) / len(chunk) > 32:  # class 0 = character boxes
+                lo = mid
+            else:
+                hi = mid
+        loc._conf_thresh = conf = hi
+        weights = "random-init YOLOv5s, confidence threshold calibrated to ~32 character boxes per line"
     chars = [chr(33 + i % 94) for i in range(rec_pipe.index.ntotal)]
     full = EffOCRPipeline(loc, rec_pipe, chars, lang="en", knn=1)
     run_effocr(lines[:2 * bl], full, batch_lines=bl)  # warm-up, through the overlapped two-batch path
     overlap = os.environ.get("EFFOCR_PIPELINE_OVERLAP", "1") != "0"  # A/B switch for the two-stream software pipeline
-    # wall clock over host + device work: three passes over the same lines, the median is reported (one pass is 0.2 s and a
-    # single host hiccup -- page faults, a neighbour on the box -- otherwise decides the number); all three are listed
-    passes = []
+    # wall clock over host + device work: three passes over the same lines, the median is reported (a single host hiccup --
+    # page faults, a neighbour on the box -- otherwise decides a 0.3 s pass); all three are listed
+    passes, launches0 = [], lib.effocr_launch_count()
     for _ in range(3):
         barrier()
         t0 = time.perf_counter()
@@ -279,16 +296,94 @@ def time_pipeline_c3(args, rec_pipe, rank, barrier):
             res += batch_res
         torch.cuda.synchronize()
         passes.append(time.perf_counter() - t0)
+    launches = (lib.effocr_launch_count() - launches0) // 3
     dt = sorted(passes)[1]
     ncrops = sum(len(r["char_boxes"]) for r in res)
-    # localizer stage alone (device letterbox + YOLOv5s + NMS + boxes to host)
+    # localizer stage alone, host in / boxes out (device letterbox + YOLOv5s + NMS + boxes to host)
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for i0 in range(0, L, bl):
         full.localize(lines[i0:i0 + bl])
     torch.cuda.synchronize()
     dl = time.perf_counter() - t1
-    return {"lines": L, "crops": ncrops, "seconds": dt, "pass_seconds": passes, "localizer_seconds": dl, "conf_thresh": hi}
+    # the YOLOv5s forward alone on the device (CUDA events; the roofline figure of the localizer)
+    chunk = lines[:bl]
+    px, im, _ = ops.pack_images(chunk)
+    x = ops.letterbox_resize(px, im, [c.shape[:2] for c in chunk], 640, 640)
+    for _ in range(2):
+        loc._eng_net.forward(x)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        loc._eng_net.forward(x)
+    e1.record()
+    torch.cuda.synchronize()
+    yolo_ms = e0.elapsed_time(e1) / 5
+    out = {"lines": L, "crops": ncrops, "seconds": dt, "pass_seconds": passes, "localizer_seconds": dl, "conf_thresh": conf,
+           "weights": weights, "precision": precision, "launches_per_pass": int(launches), "yolo_ms_per_64_lines": yolo_ms,
+           "tracking": tracking, "h2d_bytes_per_line": int(lines[0].nbytes), "parity": None}
+    # parity of the WHOLE path against the CPU oracle (letterbox -> YOLOv5s fp32 -> NMS -> reference box logic -> transform ->
+    # ViT-S fp32 -> IndexFlatIP) on the first lines of the job: strings must be identical (CER vs the reference path = 0)
+    if trained and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from effocr_b200 import textproc
+        from oracle import pipeline as OP
+
+        n_chk = 8
+        t2 = time.perf_counter()
+        ref = OP.run(lines[:n_chk], ysd, rec_pipe._state_for_oracle, index_vectors, chars, conf_thres=0.35, iou_thres=0.01, k=1)
+        cpu_s = time.perf_counter() - t2
+        pairs = [((r["text"] or ""), (g["text"] or "")) for r, g in zip(ref, res[:n_chk])]
+        acc, cer = textproc.textline_evaluation(pairs)
+        same_rects = sum(tuple(a) == tuple(b) for r, g in zip(ref, res[:n_chk]) for a, b in zip(r["rects"], g["rects"]))
+        n_rects = sum(len(r["rects"]) for r in ref)
+        counts_equal = all(len(r["rects"]) == len(g["rects"]) and r["word_end_idx"] == g["word_end_idx"] for r, g in zip(ref, res[:n_chk]))
+        # character by character: every character whose oracle top-1 / top-2 margin exceeds 4e-3 (SURVEY.md 8c rule 3; 99 %
+        # of them with the quick-fit weights against the 10 000-glyph index) must be the same glyph
+        dec = same = 0
+        if counts_equal:
+            for r, g in zip(ref, res[:n_chk]):
+                for cr, cg, m in zip(r["nns"], g["nns"], r["margin"]):
+                    if m > 4e-3:
+                        dec += 1
+                        same += int(cr[:1] == cg[:1])
+        out["parity"] = {"lines_checked": n_chk, "characters": n_rects, "strings_identical_pct": acc, "cer_vs_oracle": cer,
+                         "crop_rectangles_identical": same_rects / max(n_rects, 1), "boxes_and_word_ends_equal": counts_equal,
+                         "decidable_characters": dec, "decidable_identical": same,
+                         "cpu_oracle_lines_per_s": n_chk / cpu_s,
+                         "ok": bool(counts_equal and dec >= 0.95 * n_rects and same == dec)}
+    return out, full
+
+
+def time_paths_c5(args, full, rank, world, barrier):
+    """BASELINE config C5's mechanism on this node: PNG line files on disk -> lineio.run_effocr_paths_sharded (every rank
+    decodes and transcribes its shard of the path list, one gather_object of the records to rank 0, no steady-state
+    collective) -> inference_results.  `--paths-lines` paths per GPU over 256 distinct rendered lines."""
+    import tempfile
+
+    from effocr_b200 import lineio, synth
+
+    n_unique, per_gpu = 256, args.paths_lines
+    root = os.path.join(tempfile.gettempdir(), f"effocr_b200_c5_{os.environ.get('MASTER_PORT', '0')}")
+    if rank == 0:
+        from PIL import Image
+
+        os.makedirs(root, exist_ok=True)
+        for i, l in enumerate(synth.synthetic_lines(n_unique, seed=5000, tracking=4.0)):
+            Image.fromarray(l[0]).save(os.path.join(root, f"line_{i:04d}.png"))
+    barrier()
+    files = [os.path.join(root, f"line_{i:04d}.png") for i in range(n_unique)]
+    paths = [files[i % n_unique] for i in range(per_gpu * world)]
+    lineio.run_effocr_paths_sharded(paths[:128 * world], full, batch_lines=64)  # warm-up (decoder threads, allocator)
+    barrier()
+    t0 = time.perf_counter()
+    results, _coco = lineio.run_effocr_paths_sharded(paths, full, batch_lines=64)
+    barrier()
+    dt = time.perf_counter() - t0
+    ok = None
+    if rank == 0:
+        ok = len(results) > 0.9 * n_unique and all(isinstance(v, str) for v in results.values())
+    return {"paths": len(paths), "seconds": dt, "distinct_lines": n_unique, "transcribed_keys": len(results) if rank == 0 else None,
+            "ok": ok}
 
 
 def main():
@@ -433,9 +528,12 @@ def main():
 
     # ---- auxiliary: the WHOLE hot path (BASELINE config C3: YOLOv5s localizer + ViT-S + kNN) on synthetic 64x1024 lines,
     # host line images in, transcriptions out (wall clock around run_effocr, H2D / D2H / host box logic included)
-    pipe_block = None
+    pipe_block = paths_block = None
     if args.pipeline_lines > 0:
-        pipe_block = time_pipeline_c3(args, pipe, rank, barrier)
+        pipe._state_for_oracle = sd
+        pipe_block, full_pipe = time_pipeline_c3(args, pipe, rank, world, barrier, index_vectors.cpu())
+        if args.paths_lines > 0:
+            paths_block = time_paths_c5(args, full_pipe, rank, world, barrier)
 
     # max over ranks
     if dist is not None:
@@ -450,14 +548,28 @@ def main():
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         sec, lsec = float(agg[0]), float(agg[1])
         nl, nc = float(tot[0]), float(tot[1])
-        pass_seconds = pipe_block["pass_seconds"]
-        pipe_block = {"workload": "config C3: YOLOv5s localizer (640x640 letterbox, iou 0.01) + ViT-S/16 + kNN k=1 on synthetic "
-                                  f"64x1024 lines, {args.pipeline_lines} lines per GPU, host u8 lines in / strings out",
+        pb, pass_seconds = pipe_block, pipe_block["pass_seconds"]
+        peak_t = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        yolo_tf = YOLO_FLOPS_PER_LINE_640 * 64 / (pb["yolo_ms_per_64_lines"] / 1e3) / 1e12
+        pipe_block = {"workload": "BASELINE config 3: YOLOv5s localizer (640x640 letterbox, conf 0.35 / iou 0.01) + ViT-S/16 + kNN k=1 "
+                                  f"end to end on synthetic 64x1024 lines, {args.pipeline_lines} lines per GPU in batches of 64, "
+                                  "host u8 lines in / strings out",
+                      "metric": "char-crops/sec end-to-end (localize+embed+kNN)",
                       "lines": int(nl), "crops": int(nc), "crops_per_line": nc / max(nl, 1), "lines_per_s": nl / sec,
                       "crops_per_s": nc / sec, "localizer_lines_per_s": nl / lsec,
-                      "timing": "wall clock, median of three passes, max over ranks",
-                      "rank0_pass_lines_per_s": [pipe_block["lines"] / t for t in pass_seconds],
-                      "conf_thresh_calibrated": pipe_block["conf_thresh"]}
+                      "timing": "wall clock around EffOCRPipeline.infer_batches (H2D of the u8 lines, host box logic, D2H of boxes and ids "
+                                "inside), median of three passes, max over ranks",
+                      "rank0_pass_lines_per_s": [pb["lines"] / t for t in pass_seconds],
+                      "weights": pb["weights"], "localizer_precision": pb["precision"], "letter_spacing_px": pb["tracking"],
+                      "conf_thresh": pb["conf_thresh"], "gpu_launches_per_pass": pb["launches_per_pass"],
+                      "e2e": {"value": nc / sec, "unit": "crops/s", "h2d_bytes_per_step": pb["h2d_bytes_per_line"] * 64,
+                              "d2h_bytes_per_step": 64 * 1000 * 6 * 4 + int(nc / max(nl, 1) * 64) * 8, "step": "one batch of 64 lines"},
+                      "roofline_localizer": {"kernel": "YOLOv5s forward (all layers), 64 letterboxed lines", "bound": "tensor",
+                                             "achieved": yolo_tf, "peak": peak_t, "unit": "TFLOP/s", "frac": yolo_tf / peak_t,
+                                             "ms_per_64_lines": pb["yolo_ms_per_64_lines"],
+                                             "note": "algorithmic FLOPs of the reference model (15.76 GFLOP per line); the split-precision "
+                                                     "mode executes three tensor-core products per convolution"},
+                      "parity": pb["parity"]}
     total_crops = B * world * args.steps
     value = total_crops / (ms_dev / 1e3)
     e2e_value = total_crops / (ms_e2e / 1e3)
@@ -559,9 +671,18 @@ def main():
             line["cpu_baseline"] = cpu_block
         if pipe_block is not None:
             line["pipeline_c3"] = pipe_block
+        if paths_block is not None:
+            line["paths_c5"] = {"workload": "BASELINE config 5 mechanism: PNG line files -> lineio.run_effocr_paths_sharded (thread-pool decode, "
+                                            f"lines sharded over {world} rank(s), records gathered on rank 0), {args.paths_lines} paths per GPU",
+                                "paths": paths_block["paths"], "lines_per_s": paths_block["paths"] / paths_block["seconds"],
+                                "seconds": paths_block["seconds"], "distinct_lines": paths_block["distinct_lines"],
+                                "transcribed_keys": paths_block["transcribed_keys"], "timing": "wall clock between barriers (decode + GPU + gather)",
+                                "ok": paths_block["ok"]}
         print(json.dumps(line), flush=True)
         if cpu_block is not None and not cpu_block["parity"]["ok"]:
             raise SystemExit(f"bench.py: parity against the CPU oracle FAILED: {cpu_block['parity']}")
+        if pipe_block is not None and pipe_block.get("parity") and not pipe_block["parity"]["ok"]:
+            raise SystemExit(f"bench.py: whole-pipeline parity against the CPU oracle FAILED: {pipe_block['parity']}")
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -63,6 +63,7 @@ SIGNATURES = {
     "effocr_attention_f16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "effocr_yolo_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "effocr_yolo_destroy": (None, [c_void_p]),
+    "effocr_yolo_set_mode": (c_int, [c_void_p, c_int]),
     "effocr_yolo_num_predictions": (c_int, [c_int, c_int]),
     "effocr_yolo_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_nms": (c_int, [c_void_p, c_int, c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p]),

@@ -66,12 +66,19 @@ struct Conv3Params {
   const float* bias;      // [Cout] folded BN bias
   const __half* resid;    // optional residual (same pixel grid as the output), pixel pitch ld_res
   int ld_res;
+  long long lo_off;       // SPLIT: element offset from a tensor's hi plane to its lo plane (residual)
+  int kdim;               // SPLIT: columns of one weight plane (9 * C); the lo plane follows at column kdim
 };
 
-template <int BLOCK_N, int CB>
+// SPLIT (the localizer's reference-accurate mode, see yolo.cu): activations are (hi, lo) fp16 plane pairs, weights are
+// [Whi | Wlo]; the K loop runs three segments -- hi x Whi, lo x Whi, hi x Wlo -- into the same fp32 accumulator, i.e. the
+// fp32 product up to 2^-22, and the epilogue splits its fp32 result into the two output planes.  Only the producer's
+// choice of tensor map / weight column and the epilogue differ; the MMA loop just runs 3x as many k-blocks.
+template <int BLOCK_N, int CB, bool SPLIT = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv3_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constant__ CUtensorMap tma_w,
-                const __grid_constant__ CUtensorMap tma_out, Conv3Params p) {
+                const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_in_lo,
+                const __grid_constant__ CUtensorMap tma_out_lo, Conv3Params p) {
   using Cfg = Conv3Cfg<BLOCK_N, CB>;
   constexpr int STAGES = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -118,6 +125,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
   const int num_tiles = p.B * tiles_h * tiles_w * num_n;
   const int cblocks = p.C / CB;
   const int num_kb = 9 * cblocks;
+  constexpr int SEGS = SPLIT ? 3 : 1;
 
   auto decode = [&](int tile, int& b, int& oh0, int& ow0, int& n0) {
     n0 = (tile % num_n) * BLOCK_N;
@@ -135,16 +143,17 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int b, oh0, ow0, n0;
         decode(tile, b, oh0, ow0, n0);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / cblocks, cb = kb - tap * cblocks;
-          const int ky = tap / 3, kx = tap - ky * 3;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(&tma_in, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * CB, ow0 * p.stride - 1 + kx,
-                      oh0 * p.stride - 1 + ky, b);
-          tma_load_2d(&tma_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes, tap * p.C + cb * CB, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+        for (int seg = 0; seg < SEGS; ++seg)
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int tap = kb / cblocks, cb = kb - tap * cblocks;
+            const int ky = tap / 3, kx = tap - ky * 3;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(seg == 1 ? &tma_in_lo : &tma_in, &full_bar[stage], smem_a + stage * Cfg::kABytes, cb * CB,
+                        ow0 * p.stride - 1 + kx, oh0 * p.stride - 1 + ky, b);
+            tma_load_2d(&tma_w, &full_bar[stage], smem_b + stage * Cfg::kBBytes, (seg == 2 ? p.kdim : 0) + tap * p.C + cb * CB, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
       }
     }
   } else if (warp_idx == 1) {
@@ -161,7 +170,7 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < SEGS * num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         const uint64_t da = CB == 64 ? make_sw128_kmajor_desc(a_base + stage * Cfg::kABytes)
@@ -223,36 +232,50 @@ conv3_tc_kernel(const __grid_constant__ CUtensorMap tma_in, const __grid_constan
         if (p.resid && pix_ok) {
           const __half* r = p.resid + ((static_cast<long long>(b) * p.Ho + oh) * p.Wo + ow) * p.ld_res + col0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(r + 8 * j);
-            const __half2* hp = reinterpret_cast<const __half2*>(&u);
+          for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {  // SPLIT: the residual is hi + lo
+            const __half* rp = r + (pl ? p.lo_off : 0);
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 f = __half22float2(hp[t]);
-              y[8 * j + 2 * t] += f.x;
-              y[8 * j + 2 * t + 1] += f.y;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(rp + 8 * j);
+              const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(hp[t]);
+                y[8 * j + 2 * t] += f.x;
+                y[8 * j + 2 * t + 1] += f.y;
+              }
             }
           }
         }
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        uint8_t* dst = stg + buf * Cfg::kWarpStagingBytes;
-        // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 pk;
-          __half2* ph = reinterpret_cast<__half2*>(&pk);
+        for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* dst = stg + buf * Cfg::kWarpStagingBytes;
+          // 64-byte rows, SWIZZLE_64B: 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
 #pragma unroll
-          for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
-          *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+          for (int j = 0; j < 4; ++j) {
+            uint4 pk;
+            __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
+              if (SPLIT && pl == 0) {  // what the hi plane could not hold goes to the lo plane
+                const float2 f = __half22float2(ph[t]);
+                y[8 * j + 2 * t] -= f.x;
+                y[8 * j + 2 * t + 1] -= f.y;
+              }
+            }
+            *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(pl ? &tma_out_lo : &tma_out, dst, col0, ow0, oh0 + 2 * q, b);
+            tma_store_commit();
+          }
+          buf ^= 1;
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&tma_out, dst, col0, ow0, oh0 + 2 * q, b);
-          tma_store_commit();
-        }
-        buf ^= 1;
       }
     }
     if (lane == 0) tma_store_wait_all<0>();

@@ -38,9 +38,11 @@ __global__ void __launch_bounds__(256) cnx_im2patch4_kernel(const float* __restr
     const int c = piece / 4, iy = piece % 4;
     const int py = p / 56, px = p % 56;
     const float4 a = *reinterpret_cast<const float4*>(img + ((static_cast<long long>(b) * 3 + c) * 224 + py * 4 + iy) * 224 + px * 4);
+    // white-centred patch rows (see crop.cu): the stem bias carries W . white
+    const float wl = c == 0 ? (1.0f - 0.485f) / 0.229f : (c == 1 ? (1.0f - 0.456f) / 0.224f : (1.0f - 0.406f) / 0.225f);
     uint2 pk;
-    *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(a.x, a.y);
-    *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(a.z, a.w);
+    *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(a.x - wl, a.y - wl);
+    *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(a.z - wl, a.w - wl);
     *reinterpret_cast<uint2*>(out + prow * 48 + piece * 4) = pk;
   }
 }
@@ -326,7 +328,18 @@ extern "C" int effocr_convnext_create(int max_batch, const float* const* hw, int
   };
   do {
     if ((st = h->up16(&h->stem_w, to16(hw[i], 96 * 48)))) break; ++i;
-    if ((st = h->up32(&h->stem_b, hw[i], 96))) break; ++i;
+    {
+      // the 4x4-patch rows are white-centred (crop.cu): bias' = bias + sum_k fp16(W[n, k]) * white(channel of k), k = c*16 + ...
+      const float white[3] = {(1.0f - 0.485f) / 0.229f, (1.0f - 0.456f) / 0.224f, (1.0f - 0.406f) / 0.225f};
+      std::vector<float> b(96);
+      for (int n = 0; n < 96; ++n) {
+        double acc = hw[i][n];
+        for (int k = 0; k < 48; ++k)
+          acc += static_cast<double>(__half2float(__float2half_rn(hw[i - 1][n * 48 + k]))) * static_cast<double>(white[k / 16]);
+        b[n] = static_cast<float>(acc);
+      }
+      if ((st = h->up32(&h->stem_b, b.data(), 96))) break; ++i;
+    }
     if ((st = h->up32(&h->stem_ln_w, hw[i], 96))) break; ++i;
     if ((st = h->up32(&h->stem_ln_b, hw[i], 96))) break; ++i;
     for (int sidx = 0; sidx < 4 && !st; ++sidx) {

@@ -55,6 +55,8 @@ __device__ __forceinline__ void numpy_slice(int start, int stop, int n, int* lo,
 constexpr int kCropMaxStage = 3072;  // staged source pixels (float4 each) per block: 48 KB
 constexpr int kCropSmemBytes = kCropMaxStage * 16 + 224 * 16 + 224 * 4;  // 53 KB: four blocks per SM
 
+constexpr float kWhiteR = (1.0f - 0.485f) / 0.229f, kWhiteG = (1.0f - 0.456f) / 0.224f, kWhiteB = (1.0f - 0.406f) / 0.225f;
+
 template <int LAYOUT>  // 0 NCHW f16, 1 NCHW f32, 2 patch-major f16 ([n*196, 768], ViT/16), 3 4x4-patch-major f16 ([n*3136, 48])
 __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restrict__ pixels,
                                                           const effocr_image_desc* __restrict__ images,
@@ -223,6 +225,19 @@ __global__ void __launch_bounds__(224) crop_resize_kernel(const uint8_t* __restr
       acc[0][k] = (r - 0.485f) / 0.229f;
       acc[1][k] = (g - 0.456f) / 0.224f;
       acc[2][k] = (b - 0.406f) / 0.225f;
+    }
+  }
+  if (LAYOUT >= 2) {
+    // patch-major fp16 layouts are WHITE-CENTRED: the value stored is (normalised - white level).  A character crop is
+    // mostly white padding / background, and the white level (2.2489, 2.4286, 2.6400) is not an fp16 number: its rounding
+    // error (up to 8.6e-4, the same sign on every white pixel) adds up coherently in the patch-embedding sums and was
+    // 90 % of the encoder's embedding error.  Centred, white is exactly 0; the encoders add W . white to their
+    // patch-embedding bias instead (vit.cu / convnext.cu).  An empty rectangle (the reference's all-zero crop) is -white.
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[0][k] -= kWhiteR;
+      acc[1][k] -= kWhiteG;
+      acc[2][k] -= kWhiteB;
     }
   }
   // the selection below is resolved at compile time, indices are static after unrolling

@@ -292,7 +292,18 @@ extern "C" int effocr_vit_create(int embed_dim, int num_heads, int depth, int ml
   auto W = [&](int i) { return h_weights[i]; };
   do {
     if ((st = v->upload_f16(&v->w_patch, W(0), size_t(D) * 768))) break;
-    if ((st = v->upload_f32(&v->b_patch, W(1), D))) break;
+    {
+      // the patch rows are white-centred (crop.cu): bias' = bias + sum_k fp16(W[n, k]) * white(channel of k)
+      const float white[3] = {(1.0f - 0.485f) / 0.229f, (1.0f - 0.456f) / 0.224f, (1.0f - 0.406f) / 0.225f};
+      std::vector<float> b(D);
+      for (int n = 0; n < D; ++n) {
+        double acc = W(1)[n];
+        for (int k = 0; k < 768; ++k)
+          acc += static_cast<double>(__half2float(__float2half_rn(W(0)[size_t(n) * 768 + k]))) * static_cast<double>(white[k / 256]);
+        b[n] = static_cast<float>(acc);
+      }
+      if ((st = v->upload_f32(&v->b_patch, b.data(), D))) break;
+    }
     if ((st = v->upload_f32(&v->cls, W(2), D))) break;
     if ((st = v->upload_f32(&v->pos, W(3), size_t(197) * D))) break;
     v->layers.resize(depth);

@@ -94,11 +94,13 @@ __global__ void __launch_bounds__(256) im2patch_kernel(const float* __restrict__
     const float* src = img + ((static_cast<long long>(b) * 3 + c) * 224 + py * 16 + iy) * 224 + px * 16 + ix0;
     const float4 a = *reinterpret_cast<const float4*>(src);
     const float4 d = *reinterpret_cast<const float4*>(src + 4);
+    // white-centred patch rows (see crop.cu): the encoder's patch-embedding bias carries W . white
+    const float wl = c == 0 ? (1.0f - 0.485f) / 0.229f : (c == 1 ? (1.0f - 0.456f) / 0.224f : (1.0f - 0.406f) / 0.225f);
     uint4 pk;
-    *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(a.x, a.y);
-    *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(a.z, a.w);
-    *reinterpret_cast<__half2*>(&pk.z) = __floats2half2_rn(d.x, d.y);
-    *reinterpret_cast<__half2*>(&pk.w) = __floats2half2_rn(d.z, d.w);
+    *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(a.x - wl, a.y - wl);
+    *reinterpret_cast<__half2*>(&pk.y) = __floats2half2_rn(a.z - wl, a.w - wl);
+    *reinterpret_cast<__half2*>(&pk.z) = __floats2half2_rn(d.x - wl, d.y - wl);
+    *reinterpret_cast<__half2*>(&pk.w) = __floats2half2_rn(d.z - wl, d.w - wl);
     *reinterpret_cast<uint4*>(out + prow * 768 + vec * 8) = pk;
   }
 }

@@ -18,6 +18,7 @@
 #include "../../include/effocr_b200.h"
 #include "gemm.h"
 #include "conv3_sm100.cuh"
+#include "yolo_split_sm100.cuh"
 
 namespace effocr {
 
@@ -303,6 +304,8 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
 // ------------------------------------------------------------------ host side
 struct ConvW {
   __half* w = nullptr;  // [cout, kdim] fp16, BN folded, k>1: (ky, kx, cin) column order (layer 0: torch order)
+  __half* w2 = nullptr; // split mode: [cout, 2 * kdim] = [Whi | Wlo] (layer 0: unused)
+  float* wf = nullptr;  // split mode, layer 0 only: [108][32] fp32, k-major
   float* b = nullptr;   // [cout] fp32 folded BN bias
   int cin = 0, cout = 0, k = 1, s = 1, kdim = 0;
 };
@@ -314,8 +317,11 @@ struct Act {
 
 struct YoloHandle {
   int nc = 2, no = 7, max_batch = 0, max_h = 0, max_w = 0, ldr = 24;
+  int mode = EFFOCR_YOLO_SPLIT;  // EFFOCR_YOLO_SPLIT (reference-accurate, default) | EFFOCR_YOLO_FP16 (fast)
+  long long lo_off = 0;          // element offset from an activation's hi plane to its lo plane (= arena_elems)
   std::vector<ConvW> convs;
   __half* det_w[3] = {nullptr, nullptr, nullptr};
+  __half* det_w2[3] = {nullptr, nullptr, nullptr};  // [3 * no, 2 * C] = [Whi | Wlo]
   float* det_b[3] = {nullptr, nullptr, nullptr};
   float anchors_px[3][3][2];
   std::vector<void*> allocs;
@@ -382,28 +388,34 @@ static inline int grid_for(long long total) {
   return static_cast<int>(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
-template <int BN, int CB>
+template <int BN, int CB, bool SPLIT = false>
 static int launch_conv3(const __half* in, int ld_in, int B, int H, int W, int C, const __half* w, int kdim, const float* bias,
-                        int Cout, int stride, __half* out, int ld_out, const __half* resid, int ld_res, cudaStream_t s) {
+                        int Cout, int stride, __half* out, int ld_out, const __half* resid, int ld_res, cudaStream_t s,
+                        long long lo_off = 0) {
   using Cfg = Conv3Cfg<BN, CB>;
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  CUtensorMap tin, tw, tout;
+  CUtensorMap tin, tw, tout, tin_lo, tout_lo;
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(W), static_cast<uint64_t>(H), static_cast<uint64_t>(B)};
     const uint64_t st[3] = {static_cast<uint64_t>(ld_in) * 2, static_cast<uint64_t>(W) * ld_in * 2, static_cast<uint64_t>(H) * W * ld_in * 2};
     const uint32_t box[4] = {CB, static_cast<uint32_t>(kConvTW * stride), static_cast<uint32_t>(kConvTH * stride), 1};
     const uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
     EFFOCR_TRY(make_tmap_4d(&tin, in, 2, dims, st, box, es, CB * 2));
+    if (SPLIT) EFFOCR_TRY(make_tmap_4d(&tin_lo, in + lo_off, 2, dims, st, box, es, CB * 2));
+    else tin_lo = tin;
   }
-  EFFOCR_TRY(make_tmap_2d(&tw, w, 2, Cout, kdim, kdim, BN, CB, CB * 2));
+  // SPLIT: `w` is [Cout, 2 * kdim] = [Whi | Wlo]
+  EFFOCR_TRY(make_tmap_2d(&tw, w, 2, Cout, SPLIT ? 2 * kdim : kdim, SPLIT ? 2 * kdim : kdim, BN, CB, CB * 2));
   {
     const uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(B)};
     const uint64_t st[3] = {static_cast<uint64_t>(ld_out) * 2, static_cast<uint64_t>(Wo) * ld_out * 2, static_cast<uint64_t>(Ho) * Wo * ld_out * 2};
     const uint32_t box[4] = {32, kConvTW, 2, 1};
     const uint32_t es[4] = {1, 1, 1, 1};
     EFFOCR_TRY(make_tmap_4d(&tout, out, 2, dims, st, box, es, 64));
+    if (SPLIT) EFFOCR_TRY(make_tmap_4d(&tout_lo, out + lo_off, 2, dims, st, box, es, 64));
+    else tout_lo = tout;
   }
-  auto kern = conv3_tc_kernel<BN, CB>;
+  auto kern = conv3_tc_kernel<BN, CB, SPLIT>;
   static bool attr_done = false;
   if (!attr_done) {
     EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -411,14 +423,59 @@ static int launch_conv3(const __half* in, int ld_in, int B, int H, int W, int C,
   }
   Conv3Params p;
   p.B = B; p.Ho = Ho; p.Wo = Wo; p.C = C; p.Cout = Cout; p.stride = stride; p.bias = bias; p.resid = resid; p.ld_res = ld_res;
+  p.lo_off = lo_off; p.kdim = kdim;
   const int tiles = B * ((Ho + kConvTH - 1) / kConvTH) * ((Wo + kConvTW - 1) / kConvTW) * ((Cout + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   {
     KernelScope ks(PROF_GEMM_OTHER, s);
-    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tin, tw, tout, p);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(tin, tw, tout, tin_lo, tout_lo, p);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;
+}
+
+// 1x1 convolution / Detect head in split precision: out = act(A . W^T + bias) with A = (hi, lo) planes, W2 = [Whi | Wlo]
+template <int BN, bool F32, int ACT>
+static int launch_split3_bn(const __half* A, long long lda, long long lo_off, const __half* w2, int M, int N, int K,
+                            const float* bias, void* out, long long ldo, cudaStream_t s) {
+  using Cfg = GemmTmaCfg<BN, F32>;
+  CUtensorMap ta, tal, tw, tc, tcl;
+  EFFOCR_TRY(make_tmap_f16_2d(&ta, A, M, K, lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tal, A + lo_off, M, K, lda, kBlockM));
+  EFFOCR_TRY(make_tmap_f16_2d(&tw, w2, N, 2 * K, 2 * K, BN));
+  if (F32) {
+    EFFOCR_TRY(make_tmap_2d(&tc, out, 4, M, N, ldo, 32, 32, 128));
+    tcl = tc;
+  } else {
+    EFFOCR_TRY(make_tmap_2d(&tc, out, 2, M, N, ldo, 32, 32, 64));
+    EFFOCR_TRY(make_tmap_2d(&tcl, reinterpret_cast<__half*>(out) + lo_off, 2, M, N, ldo, 32, 32, 64));
+  }
+  auto kern = gemm_split3_kernel<BN, F32, ACT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  Split3Params p;
+  p.M = M; p.N = N; p.K = K; p.bias = bias;
+  {
+    KernelScope ks(PROF_GEMM_OTHER, s);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, s>>>(ta, tal, tw, tc, tcl, p);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+template <bool F32, int ACT>
+static int launch_split3(const __half* A, long long lda, long long lo_off, const __half* w2, int M, int N, int K,
+                         const float* bias, void* out, long long ldo, cudaStream_t s) {
+  switch (choose_block_n(N)) {
+    case 64: return launch_split3_bn<64, F32, ACT>(A, lda, lo_off, w2, M, N, K, bias, out, ldo, s);
+    case 128: return launch_split3_bn<128, F32, ACT>(A, lda, lo_off, w2, M, N, K, bias, out, ldo, s);
+    case 192: return launch_split3_bn<192, F32, ACT>(A, lda, lo_off, w2, M, N, K, bias, out, ldo, s);
+    default: return launch_split3_bn<256, F32, ACT>(A, lda, lo_off, w2, M, N, K, bias, out, ldo, s);
+  }
 }
 
 struct YoloRun {
@@ -438,8 +495,14 @@ struct YoloRun {
   }
   static Act slice(Act a, int c0) { return Act{a.p + c0, a.ld}; }
 
+  bool split() const { return h->mode == EFFOCR_YOLO_SPLIT; }
   void gemm(const __half* A, int lda, long long rows, const ConvW& cw, Act out, const Act* resid) {
     if (status) return;
+    if (split() && !resid) {
+      status = launch_split3<false, ACT_SILU>(A, lda, h->lo_off, cw.w2, static_cast<int>(rows), cw.cout, cw.kdim, cw.b, out.p,
+                                              out.ld, s);
+      return;
+    }
     GemmArgs g;
     g.A = A; g.lda = lda; g.W = cw.w; g.ldw = cw.kdim; g.M = static_cast<int>(rows); g.N = cw.cout; g.K = cw.kdim;
     g.out = out.p; g.ldo = out.ld; g.bias = cw.b; g.act = 2;
@@ -462,6 +525,16 @@ struct YoloRun {
       const char* e = getenv("EFFOCR_YOLO_CONV3");  // "im2col" = explicit gather + GEMM (first version; A/B runs)
       return e && e[0] == 'i';
     }();
+    if (split()) {
+      const __half* rp = resid ? resid->p : nullptr;
+      const int rl = resid ? resid->ld : 0;
+      const long long lo = h->lo_off;
+      if (cw.cin == 32) status = launch_conv3<64, 32, true>(in.p, in.ld, B, H, W, cw.cin, cw.w2, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s, lo);
+      else if (cw.cout <= 64) status = launch_conv3<64, 64, true>(in.p, in.ld, B, H, W, cw.cin, cw.w2, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s, lo);
+      else if (cw.cout <= 128) status = launch_conv3<128, 64, true>(in.p, in.ld, B, H, W, cw.cin, cw.w2, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s, lo);
+      else status = launch_conv3<256, 64, true>(in.p, in.ld, B, H, W, cw.cin, cw.w2, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s, lo);
+      return;
+    }
     if (!use_im2col) {  // implicit GEMM: the A operand comes straight from the activation tensor through 4-D TMA boxes
       const __half* rp = resid ? resid->p : nullptr;
       const int rl = resid ? resid->ld : 0;
@@ -536,7 +609,13 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
       const char* e = getenv("EFFOCR_YOLO_STEM");  // "gemm" = explicit im2col + tcgen05 GEMM (first version; A/B runs)
       return e && e[0] == 'g';
     }();
-    if (stem_gemm) {
+    if (r.split()) {
+      const int tiles = B * ((H1 + kStemF32TH - 1) / kStemF32TH) * ((W1 + kStemF32TW - 1) / kStemF32TW);
+      const int grid = tiles < 4 * sm_count() ? tiles : 4 * sm_count();
+      KernelScope ks(PROF_YOLO_MISC, s);
+      yolo_stem_f32_kernel<<<grid, 256, 0, s>>>(img, cw.wf, cw.b, x0.p, x0.p + h->lo_off, x0.ld, B, H, W);
+      EFFOCR_CUDA(cudaGetLastError());
+    } else if (stem_gemm) {
       if (static_cast<size_t>(p1) * 112 > h->col_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small");
       {
         KernelScope ks(PROF_CONV_IM2COL, s);
@@ -562,20 +641,24 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
   r.conv1(x8, p5, YoloRun::slice(catS, 0));             // 9 SPPF cv1 -> first quarter of catS
   if (!r.status) {
     KernelScope ks(PROF_YOLO_MISC, s);
-    for (int k = 0; k < 3; ++k)  // windows 5, 9, 13 = three chained 5x5 pools
-      yolo_pool5_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, 1024, B, H5, W5, 256, k * 256, (k + 1) * 256);
+    for (int k = 0; k < 3; ++k) {  // windows 5, 9, 13 = three chained 5x5 pools
+      if (r.split()) yolo_pool5_split_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, h->lo_off, 1024, B, H5, W5, 256, k * 256, (k + 1) * 256);
+      else yolo_pool5_kernel<<<grid_for(p5 * 32), 256, 0, s>>>(catS.p, 1024, B, H5, W5, 256, k * 256, (k + 1) * 256);
+    }
   }
   r.conv1(catS, p5, x9);                                // 9 SPPF cv2
   r.conv1(x9, p5, YoloRun::slice(cat22, 256));          // 10 -> second half of cat22
   if (!r.status) {
     KernelScope ks(PROF_YOLO_MISC, s);
     yolo_upsample2x_kernel<<<grid_for(p4 * 32), 256, 0, s>>>(cat22.p + 256, 512, cat12.p, 512, B, H5, W5, 256);  // 11, 12
+    if (r.split()) yolo_upsample2x_kernel<<<grid_for(p4 * 32), 256, 0, s>>>(cat22.p + h->lo_off + 256, 512, cat12.p + h->lo_off, 512, B, H5, W5, 256);
   }
   r.c3(cat12, 256, 1, false, H4, W4, x13);              // 13
   r.conv1(x13, p4, YoloRun::slice(cat19, 128));         // 14 -> second half of cat19
   if (!r.status) {
     KernelScope ks(PROF_YOLO_MISC, s);
     yolo_upsample2x_kernel<<<grid_for(p3 * 16), 256, 0, s>>>(cat19.p + 128, 256, cat16.p, 256, B, H4, W4, 128);  // 15, 16
+    if (r.split()) yolo_upsample2x_kernel<<<grid_for(p3 * 16), 256, 0, s>>>(cat19.p + h->lo_off + 128, 256, cat16.p + h->lo_off, 256, B, H4, W4, 128);
   }
   r.c3(cat16, 128, 1, false, H3, W3, x17);              // 17
   r.conv3(x17, H3, W3, YoloRun::slice(cat19, 0));       // 18 -> first half of cat19
@@ -593,11 +676,16 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
   for (int l = 0; l < 3; ++l) {
     const long long rows = 1LL * B * nys[l] * nxs[l];
     if (static_cast<size_t>(rows) * h->ldr > h->raw_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: detect scratch too small");
-    GemmArgs g;
-    g.A = feats[l].p; g.lda = feats[l].ld; g.W = h->det_w[l]; g.ldw = chans[l]; g.M = static_cast<int>(rows);
-    g.N = 3 * h->no; g.K = chans[l]; g.out = h->raw; g.ldo = h->ldr; g.out_f32 = 1; g.bias = h->det_b[l];
-    g.prof_tag = PROF_GEMM_OTHER;
-    EFFOCR_TRY(gemm_f16(g, s));
+    if (r.split()) {
+      EFFOCR_TRY((launch_split3<true, ACT_NONE>(feats[l].p, feats[l].ld, h->lo_off, h->det_w2[l], static_cast<int>(rows), 3 * h->no,
+                                                chans[l], h->det_b[l], h->raw, h->ldr, s)));
+    } else {
+      GemmArgs g;
+      g.A = feats[l].p; g.lda = feats[l].ld; g.W = h->det_w[l]; g.ldw = chans[l]; g.M = static_cast<int>(rows);
+      g.N = 3 * h->no; g.K = chans[l]; g.out = h->raw; g.ldo = h->ldr; g.out_f32 = 1; g.bias = h->det_b[l];
+      g.prof_tag = PROF_GEMM_OTHER;
+      EFFOCR_TRY(gemm_f16(g, s));
+    }
     {
       KernelScope ks(PROF_YOLO_MISC, s);
       yolo_decode_kernel<<<grid_for(rows * 3), 256, 0, s>>>(h->raw, h->ldr, pred, B, nys[l], nxs[l], h->no, total_preds, off,
@@ -653,6 +741,32 @@ extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, c
     if ((st = h->alloc(&cw.b, bias.size()))) break;
     cudaMemcpy(cw.w, wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(cw.b, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice);
+    // split mode: the folded fp32 weight as [Whi | Wlo] (layer 0: the fp32 matrix itself, k-major)
+    if (sp.k == 6) {
+      std::vector<float> wf(static_cast<size_t>(108) * 32);
+      for (int o = 0; o < sp.cout; ++o) {
+        const float scale = g[o] / sqrtf(var[o] + 1e-3f);
+        for (int c = 0; c < 3; ++c)
+          for (int t = 0; t < 36; ++t) wf[static_cast<size_t>(c * 36 + t) * 32 + o] = w[(static_cast<size_t>(o) * 3 + c) * 36 + t] * scale;
+      }
+      if ((st = h->alloc(&cw.wf, wf.size()))) break;
+      cudaMemcpy(cw.wf, wf.data(), wf.size() * 4, cudaMemcpyHostToDevice);
+    } else {
+      std::vector<__half> w2(static_cast<size_t>(sp.cout) * 2 * cw.kdim);
+      for (int o = 0; o < sp.cout; ++o) {
+        const float scale = g[o] / sqrtf(var[o] + 1e-3f);
+        for (int c = 0; c < sp.cin; ++c)
+          for (int t = 0; t < kk; ++t) {
+            const float v = w[(static_cast<size_t>(o) * sp.cin + c) * kk + t] * scale;
+            const size_t col = static_cast<size_t>(t) * sp.cin + c;
+            const __half hi = __float2half_rn(v);
+            w2[static_cast<size_t>(o) * 2 * cw.kdim + col] = hi;
+            w2[static_cast<size_t>(o) * 2 * cw.kdim + cw.kdim + col] = __float2half_rn(v - __half2float(hi));
+          }
+      }
+      if ((st = h->alloc(&cw.w2, w2.size()))) break;
+      cudaMemcpy(cw.w2, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice);
+    }
     h->convs.push_back(cw);
   }
   const int chans[3] = {128, 256, 512};
@@ -667,6 +781,18 @@ extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, c
     if ((st = h->alloc(&h->det_w[l], wh.size()))) break;
     if ((st = h->alloc(&h->det_b[l], static_cast<size_t>(h->ldr)))) break;
     cudaMemcpy(h->det_w[l], wh.data(), wh.size() * 2, cudaMemcpyHostToDevice);
+    {
+      std::vector<__half> w2(static_cast<size_t>(n) * 2 * chans[l]);
+      for (int o = 0; o < n; ++o)
+        for (int c = 0; c < chans[l]; ++c) {
+          const float v = w[static_cast<size_t>(o) * chans[l] + c];
+          const __half hi = __float2half_rn(v);
+          w2[static_cast<size_t>(o) * 2 * chans[l] + c] = hi;
+          w2[static_cast<size_t>(o) * 2 * chans[l] + chans[l] + c] = __float2half_rn(v - __half2float(hi));
+        }
+      if ((st = h->alloc(&h->det_w2[l], w2.size()))) break;
+      cudaMemcpy(h->det_w2[l], w2.data(), w2.size() * 2, cudaMemcpyHostToDevice);
+    }
     cudaMemset(h->det_b[l], 0, h->ldr * 4);
     cudaMemcpy(h->det_b[l], b, n * 4, cudaMemcpyHostToDevice);
     const float* an = h_weights[base + 6];  // [3,3,2] in stride units (ultralytics buffer `anchors`)
@@ -681,8 +807,9 @@ extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, c
     // activation arena: long-lived buffers (33.5 elements per input pixel) + the largest C3 scratch
     // (10 per pixel, at stride 4) + per-buffer 128-element rounding
     h->arena_elems = px * 48 + (1u << 20);
+    h->lo_off = static_cast<long long>(h->arena_elems);  // the lo planes of all activations: a second arena right behind the first
     h->raw_elems = px / 64 * h->ldr + 4096;
-    if (!(st = h->alloc(&h->col, h->col_elems)) && !(st = h->alloc(&h->arena, h->arena_elems))) st = h->alloc(&h->raw, h->raw_elems);
+    if (!(st = h->alloc(&h->col, h->col_elems)) && !(st = h->alloc(&h->arena, 2 * h->arena_elems))) st = h->alloc(&h->raw, h->raw_elems);
   }
   if (!st && cudaDeviceSynchronize() != cudaSuccess) st = fail(EFFOCR_ERR_CUDA, "yolo_create: upload failed");
   if (st) { delete h; return st; }
@@ -691,6 +818,13 @@ extern "C" int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, c
 }
 
 extern "C" void effocr_yolo_destroy(effocr_yolo_t h) { delete reinterpret_cast<YoloHandle*>(h); }
+
+extern "C" int effocr_yolo_set_mode(effocr_yolo_t handle, int mode) {
+  YoloHandle* h = reinterpret_cast<YoloHandle*>(handle);
+  if (!h || (mode != EFFOCR_YOLO_SPLIT && mode != EFFOCR_YOLO_FP16)) return fail(EFFOCR_ERR_INVALID, "yolo_set_mode: bad handle / mode");
+  h->mode = mode;
+  return EFFOCR_OK;
+}
 
 extern "C" int effocr_yolo_num_predictions(int height, int width) {
   if (height % 32 || width % 32) return -1;

@@ -109,10 +109,15 @@ def letterbox_plan(shapes, new_shape=(640, 640)):
     return plans, np.ascontiguousarray(np.concatenate(tables, 0))
 
 
-class YoloEngine:
-    """Device-resident YOLOv5s (fp16 NHWC activations, folded BN) behind effocr_yolo_*."""
+YOLO_SPLIT, YOLO_FP16 = 0, 1  # include/effocr_b200.h: EFFOCR_YOLO_SPLIT / EFFOCR_YOLO_FP16
 
-    def __init__(self, state_dict, max_batch=16, max_shape=(640, 640)):
+
+class YoloEngine:
+    """Device-resident YOLOv5s (NHWC activations, folded BN) behind effocr_yolo_*.
+    precision: "split" (default) -- (hi, lo) fp16 plane pairs and [Whi | Wlo] weights, fp32-accurate like the reference's
+    onnxruntime session; "fp16" -- single fp16 plane, about twice as fast, boxes within ~1 px of fp32."""
+
+    def __init__(self, state_dict, max_batch=16, max_shape=(640, 640), precision="split"):
         self._lib = _lib.load()
         _lib.require_device()
         sd = state_dict
@@ -130,6 +135,13 @@ class YoloEngine:
         self._h = h
         self._lock = threading.Lock()
         self.max_batch = max_batch
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str) -> None:
+        if precision not in ("split", "fp16"):
+            raise ValueError("precision must be 'split' or 'fp16'")
+        _lib.check(self._lib.effocr_yolo_set_mode(self._h, YOLO_SPLIT if precision == "split" else YOLO_FP16), "effocr_yolo_set_mode")
+        self.precision = precision
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -169,12 +181,12 @@ def nms_device(pred: torch.Tensor, conf_thres: float, iou_thres: float, max_det:
 class EffLocalizer:
 
     def __init__(self, model_path, iou_thresh=0.01, conf_thresh=0.30, vertical=False, num_cores=None, providers=None,
-                 input_shape=(640, 640), model_backend="yolo", max_batch=16):
+                 input_shape=(640, 640), model_backend="yolo", max_batch=16, precision="split"):
         if model_backend != "yolo":
             raise NotImplementedError("Backend {} is not implemented".format(model_backend))
         if input_shape is None:  # the reference falls back to the model's own (static) shape, localizer_engine.py:38-41
             input_shape = (640, 640)
-        self._eng_net = YoloEngine(_load_state(model_path), max_batch=max_batch, max_shape=tuple(input_shape))
+        self._eng_net = YoloEngine(_load_state(model_path), max_batch=max_batch, max_shape=tuple(input_shape), precision=precision)
         self._iou_thresh = iou_thresh
         self._conf_thresh = conf_thresh
         self._vertical = vertical

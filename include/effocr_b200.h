@@ -102,6 +102,9 @@ typedef struct {
 } effocr_crop_box;
 #define EFFOCR_CROP_NCHW_F16 0  /* out: fp16 [n, 3, 224, 224] */
 #define EFFOCR_CROP_NCHW_F32 1  /* out: fp32 [n, 3, 224, 224]  (== create_paired_transform output) */
+/* The two patch-major layouts are WHITE-CENTRED: they hold (normalised value - white level), white level =
+ * ((1 - mean_c) / std_c) = (2.2489083, 2.4285715, 2.6400001): the white padding / background of a crop is then exactly 0
+ * in fp16 instead of carrying the same rounding error on every pixel; the encoders fold W . white into their bias. */
 #define EFFOCR_CROP_PATCH_F16 2 /* out: fp16 [n * 196, 768] patch-major (input of effocr_vit_forward) */
 #define EFFOCR_CROP_PATCH4_F16 3 /* out: fp16 [n * 3136, 48] 4x4-patch-major (input of effocr_convnext_forward) */
 EFFOCR_API int effocr_crop_resize(const uint8_t* d_pixels, const effocr_image_desc* d_images,
@@ -143,7 +146,7 @@ EFFOCR_API int effocr_letterbox_resize(const uint8_t* d_pixels, const effocr_ima
  * The handle owns its weights and a workspace for max_batch crops (larger batches are chunked). */
 typedef struct effocr_vit_s* effocr_vit_t;
 #define EFFOCR_INPUT_NCHW_F32 0     /* d_input: fp32 [B,3,224,224] (the reference's tensor) */
-#define EFFOCR_INPUT_PATCH_F16 1    /* d_input: fp16 [B*196,768] patch-major */
+#define EFFOCR_INPUT_PATCH_F16 1    /* d_input: fp16 [B*196,768] patch-major, white-centred (what EFFOCR_CROP_PATCH_F16 writes) */
 #define EFFOCR_INPUT_PATCH_BUFFER 2 /* input already written into effocr_vit_patch_buffer(); B <= max_batch */
 EFFOCR_API int effocr_vit_create(int embed_dim, int num_heads, int depth, int mlp_dim, int max_batch, float ln_eps,
                                  const float* const* h_weights, int n_weights, effocr_vit_t* out);
@@ -191,6 +194,15 @@ typedef struct effocr_yolo_s* effocr_yolo_t;
 EFFOCR_API int effocr_yolo_create(int nc, int max_batch, int max_h, int max_w, const float* const* h_weights,
                                   int n_weights, effocr_yolo_t* out);
 EFFOCR_API void effocr_yolo_destroy(effocr_yolo_t h);
+/* Arithmetic of the forward pass.  The reference runs the detector in fp32 (onnxruntime CPU session,
+ * localizer_engine.py:54).  EFFOCR_YOLO_SPLIT (default): every activation is a pair of fp16 planes (hi, lo) and every
+ * folded weight [Whi | Wlo]; each convolution accumulates hi x Whi + lo x Whi + hi x Wlo in one fp32 TMEM accumulator,
+ * i.e. fp32-accurate products on the fp16 tensor cores -- decoded boxes and confidences agree with the fp32 path to
+ * ~1e-5, so thresholds, NMS decisions and crop-rectangle rounding come out the same.  EFFOCR_YOLO_FP16: single fp16
+ * plane, ~2x faster, boxes within ~1 px / confidences within ~6e-3 of fp32 (a few per cent of lines then differ). */
+#define EFFOCR_YOLO_SPLIT 0
+#define EFFOCR_YOLO_FP16 1
+EFFOCR_API int effocr_yolo_set_mode(effocr_yolo_t h, int mode);
 EFFOCR_API int effocr_yolo_num_predictions(int height, int width);
 EFFOCR_API int effocr_yolo_forward(effocr_yolo_t h, const float* d_images, int batch, int height, int width,
                                    float* d_pred, void* stream);

@@ -62,7 +62,7 @@ def test_pipeline_strings_identical_to_oracle_with_localizer_in_the_loop(setup, 
           f"crop rectangles pixel-identical {frac:.4f} ({n_same}/{n_rect})")
     assert n_chars >= 15 * N_LINES, "the quick-fit localizer should find most characters"
     assert [g["text"] for g in got] == [r["text"] for r in ref], [p for p in pairs if p[0] != p[1]][:3]
-    assert [g["nns"][:1] for g in got] == [r["nns"][:1] for r in ref] or k == 1
+    assert [[n[:1] for n in g["nns"]] for g in got] == [[n[:1] for n in r["nns"]] for r in ref]  # every first neighbour
     assert cer == 0.0 and acc == 100.0
     assert frac >= 0.97, f"only {frac:.4f} of the crop rectangles equal the fp32 oracle's"
     # margins are real: with trained weights the oracle's top-1 / top-2 gap is far above the embedding tolerance
@@ -71,8 +71,11 @@ def test_pipeline_strings_identical_to_oracle_with_localizer_in_the_loop(setup, 
 
 
 def test_localizer_boxes_match_oracle_on_trained_weights(setup):
-    """SURVEY 8c rule 4: same kept set per line, coordinates close.  fp16 activations against the fp32 oracle: the
-    measured deviation is reported; the assertion is the index set and a 0.25 px bound (a crop column is 1.6 px wide)."""
+    """SURVEY 8c rule 4: same kept set per line in the same order, coordinates ~1e-3 px.  The localizer runs in its default
+    "split" precision (fp32-accurate PRODUCTS on the fp16 tensor cores).  What is left is the tensor core's own fp32
+    accumulator: tcgen05.mma adds with truncation, a bias of ~K * 6e-9 relative (tools/mma_numerics_probe.py: -2.9e-5 at
+    K = 4608), which shows up as <= 4e-4 on a confidence and a few 1e-3 px on a coordinate after 25 layers -- 17x below the
+    fp16 mode's 6e-3 / 0.9 px.  The measured deviation is printed; bounds: 1e-3 on confidences, 5e-3 px on coordinates."""
     from effocr_b200.localizer_engine import EffLocalizer
     from effocr_b200 import ops
     from oracle import pipeline as OP
@@ -82,16 +85,14 @@ def test_localizer_boxes_match_oracle_on_trained_weights(setup):
     px, im, _ = ops.pack_images(lines[:32])
     out, cnt = loc.run_device(ops.letterbox_resize(px, im, [l.shape[:2] for l in lines[:32]], 640, 640))
     out, cnt = out.cpu(), cnt.cpu().tolist()
-    worst, n = 0.0, 0
+    worst, worst_conf, n = 0.0, 0.0, 0
     for i, r in enumerate(ref):
         g = out[i, :cnt[i]]
         assert len(g) == len(r), f"line {i}: {len(g)} boxes vs {len(r)} in the oracle"
-        # same boxes, possibly in a different confidence order when two confidences are within fp16 noise: match by class + x
-        go = g[np.lexsort((g[:, 0].numpy(), g[:, 5].numpy()))]
-        ro = r[np.lexsort((r[:, 0].numpy(), r[:, 5].numpy()))]
+        go, ro = g, r  # same confidence order
         assert torch.equal(go[:, 5], ro[:, 5])
         worst = max(worst, float((go[:, :4] - ro[:, :4]).abs().max())) if len(r) else worst
-        assert float((go[:, 4] - ro[:, 4]).abs().max() if len(r) else 0.0) < 2e-2
+        worst_conf = max(worst_conf, float((go[:, 4] - ro[:, 4]).abs().max())) if len(r) else worst_conf
         n += len(r)
-    print(f"{n} boxes on 32 lines: max |coordinate difference| vs the fp32 oracle = {worst:.4f} px")
-    assert n > 32 * 15 and worst < 0.25
+    print(f"{n} boxes on 32 lines: max |coordinate difference| vs the fp32 oracle = {worst:.5f} px, max |confidence difference| = {worst_conf:.2e}")
+    assert n > 32 * 15 and worst < 5e-3 and worst_conf < 1e-3

@@ -42,21 +42,29 @@ def test_nms_batch_and_empty():
     assert int(cnt[2]) == 0
 
 
+@pytest.mark.parametrize("precision", ["split", "fp16"])
 @pytest.mark.parametrize("shape,batch", [((64, 1024), 3), ((640, 640), 1), ((96, 160), 2)])
-def test_yolov5s_forward_matches_oracle(shape, batch):
+def test_yolov5s_forward_matches_oracle(shape, batch, precision):
+    """Decoded predictions against the fp32 oracle.  "split" (the default: hi/lo fp16 planes, three tensor-core products
+    per convolution) must agree like one fp32 implementation agrees with another; "fp16" is the fast mode."""
     from effocr_b200.localizer_engine import YoloEngine
     from oracle import yolo as OY
     sd = OY.init_yolov5s_state_dict(nc=2, seed=0)
     x = torch.rand(batch, 3, *shape, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         ref = OY.yolov5s_forward(sd, x)
-    eng = YoloEngine(sd, max_batch=2, max_shape=shape)
+    eng = YoloEngine(sd, max_batch=2, max_shape=shape, precision=precision)
     out = eng.forward(x.cuda()).cpu()
     assert out.shape == ref.shape
+    box_tol, conf_tol = (1e-4, 1e-4) if precision == "split" else (2e-2, 5e-3)
+    errs = []
     for lo, hi in ((0, 2), (2, 4)):
         err = (out[..., lo:hi] - ref[..., lo:hi]).abs().max() / ref[..., lo:hi].abs().max()
-        assert err < 2e-2, (lo, err)
-    assert (out[..., 4:] - ref[..., 4:]).abs().max() < 5e-3
+        errs.append(float(err))
+        assert err < box_tol, (lo, err)
+    cerr = float((out[..., 4:] - ref[..., 4:]).abs().max())
+    print(f"yolov5s {shape} {precision}: xy rel {errs[0]:.2e}, wh rel {errs[1]:.2e}, obj/cls abs {cerr:.2e}")
+    assert cerr < conf_tol
 
 
 def test_efflocalizer_run_matches_oracle_pipeline():

@@ -32,13 +32,16 @@ def test_crop_resize_matches_oracle(layout):
     bt, n = ops.pack_boxes(boxes)
     code = {"nchw_f32": ops.CROP_NCHW_F32, "nchw_f16": ops.CROP_NCHW_F16, "patch_f16": ops.CROP_PATCH_F16}[layout]
     out = ops.crop_resize(pixels, images, bt, n, code).float().cpu().numpy()
-    if layout == "patch_f16":  # [n*196, 768] -> [n,3,224,224]
+    if layout == "patch_f16":  # [n*196, 768] -> [n,3,224,224]; the patch-major layout is white-centred (see crop.cu)
         out = out.reshape(n, 14, 14, 3, 16, 16).transpose(0, 3, 1, 4, 2, 5).reshape(n, 3, 224, 224)
-    tol = 2e-5 if layout == "nchw_f32" else 2e-3  # fp16 ulp at |x| ~ 2.6 is 2e-3 / 2
+        white = (1.0 - np.asarray(T.IMAGENET_MEAN, np.float32)) / np.asarray(T.IMAGENET_STD, np.float32)
+        out += white[None, :, None, None]  # an empty rectangle is the reference's all-zero crop: stored as -white
+    # half an fp16 ulp: 1e-3 at |x| ~ 2.6 (NCHW), 2e-3 at the centred layout's darkest ink (|x - white| up to 4.8; white is 0)
+    tol = {"nchw_f32": 2e-5, "nchw_f16": 1.1e-3, "patch_f16": 2.1e-3}[layout]
     for j, (i, x0, y0, x1, y1) in enumerate(boxes):
         crop = imgs[i][y0:y1, x0:x1, :]
         if crop.size == 0:
-            assert np.all(out[j] == 0)
+            assert np.abs(out[j]).max() <= (0 if layout != "patch_f16" else 1e-3)  # fp16(-white) + white
             continue
         ref = T.paired_transform(crop)
         assert np.abs(out[j] - ref).max() <= tol, (j, boxes[j])
@@ -58,6 +61,9 @@ def test_vit_embeddings_match_oracle(name, batch):
     assert rel <= 1e-3, rel
 
 
+V_MEAN, V_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
 def test_vit_patch_input_equals_nchw_input():
     from effocr_b200.engine import VitEngine
     from oracle import vit as V
@@ -65,7 +71,8 @@ def test_vit_patch_input_equals_nchw_input():
     eng = VitEngine(sd, max_batch=4)
     x = torch.randn(4, 3, 224, 224, generator=torch.Generator().manual_seed(2)).half().float()
     e0 = eng.forward(x.cuda())
-    patches = x.reshape(4, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(4 * 196, 768).half().cuda()
+    white = ((1.0 - torch.tensor(V_MEAN)) / torch.tensor(V_STD)).view(1, 3, 1, 1)  # patch-major inputs are white-centred
+    patches = (x - white).reshape(4, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(4 * 196, 768).half().cuda()
     e1 = eng.forward(patches)
     assert torch.equal(e0, e1)  # same kernels, same operands: bit-identical, batch-composition independent
     e2 = eng.forward(x[1:2].cuda())
@@ -149,7 +156,7 @@ def test_convnext_crop_patch4_path_equals_nchw_path():
     crops = _random_crops(rng, 4)
     pixels, images, _ = ops.pack_images(crops)
     bt, n = ops.pack_boxes([(i, 0, 0, c.shape[1], c.shape[0]) for i, c in enumerate(crops)])
-    nchw = ops.crop_resize(pixels, images, bt, n, ops.CROP_NCHW_F16).float()
+    nchw = ops.crop_resize(pixels, images, bt, n, ops.CROP_NCHW_F32)  # fp32: both paths round (value - white) once
     e0 = eng.forward(nchw)
     ops.crop_resize(pixels, images, bt, n, ops.CROP_PATCH4_F16, out=eng.patch_buffer(n))
     e1 = eng.forward(None, batch=n)
