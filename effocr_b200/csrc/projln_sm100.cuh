@@ -57,7 +57,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPlnThreads, 1)
 proj_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_w,
                     const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_h, int M,
                     const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    float eps, long long* __restrict__ dbg) {
+                    float eps, long long* __restrict__ dbg, int prefetch_flags) {
 #define PLN_DBG(slot) do { if (dbg && blockIdx.x == 0 && local == 2 && warp_idx == 4 && lane == 0) dbg[(slot)] = clock64(); } while (0)
   constexpr int D = kPlnD, KB = kPlnKB, STAGES = kPlnStages;
   extern __shared__ uint8_t smem_raw[];
@@ -110,6 +110,10 @@ proj_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = tile * 256 + static_cast<int>(rank) * 128;
+        if ((prefetch_flags & 2) && tile + num_pairs < num_tiles) {  // the next tile's att rows into L2 as well
+          const int pm0 = (tile + num_pairs) * 256 + static_cast<int>(rank) * 128;
+          for (int kb = 0; kb < KB; ++kb) tma_prefetch_l2_2d(&tma_a, kb * 64, pm0);
+        }
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kPlnStageBytes);
@@ -126,8 +130,15 @@ proj_ln_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
     // ------------------------------------------------------------------ residual ring producer (per CTA, local barriers)
     if (elect_one_sync()) {
       uint32_t local = 0;
+      const bool l2_prefetch = (prefetch_flags & 1) != 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         const int m0 = tile * 256 + static_cast<int>(rank) * 128;
+        if (l2_prefetch && tile + num_pairs < num_tiles) {
+          // pull the NEXT tile's residual rows from HBM into L2 now: its ring loads (issued as slots free up, on the
+          // epilogue's critical path) then pay an L2 hit instead of an HBM round trip
+          const int pm0 = (tile + num_pairs) * 256 + static_cast<int>(rank) * 128;
+          for (int c = 0; c < 12; ++c) tma_prefetch_l2_2d(&tma_x, c * 32, pm0);
+        }
         for (int c = 0; c < 12; ++c) {  // chunk c -> slot c % 6, the slot's use number is 2 * local + c / 6
           const int sl = c % kPlnXSlots;
           const uint32_t u = 2 * local + c / kPlnXSlots;

@@ -152,7 +152,7 @@ class _EngineBackedEncoder(torch.nn.Module):
         if getattr(self, "_engine", None) is None or self._engine_ver != ver:
             sd = {"net." + k: v for k, v in self._timm_state().items()}
             if "net.stem.0.weight" in sd:
-                eng = ConvNextEngine(sd, prefix="net.", max_batch=min(self.max_batch, 256))
+                eng = ConvNextEngine(sd, prefix="net.", max_batch=min(self.max_batch, 4096))
             else:
                 eng = VitEngine(sd, prefix="net.", max_batch=self.max_batch, ln_eps=self.ln_eps)
             object.__setattr__(self, "_engine", eng)

@@ -175,7 +175,7 @@ def make_encoder_engine(state_dict, prefix: str = "net.", max_batch: int = 1024)
     if prefix + "cls_token" in state_dict:
         return VitEngine(state_dict, prefix=prefix, max_batch=max_batch)
     if prefix + "stem.0.weight" in state_dict:
-        return ConvNextEngine(state_dict, prefix=prefix, max_batch=min(max_batch, 256))
+        return ConvNextEngine(state_dict, prefix=prefix, max_batch=min(max_batch, 4096))
     raise _lib.EffocrError("unrecognised encoder checkpoint (expected timm ViT or ConvNeXt keys)")
 
 

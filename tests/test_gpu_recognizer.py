@@ -143,7 +143,8 @@ def test_convnext_embeddings_match_oracle():
     eng = ConvNextEngine(sd, max_batch=2)
     out = eng.forward(x.cuda()).cpu()
     rel = ((out - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
-    assert rel <= 2e-3, rel  # 18 blocks of fp16 operands; the ViT bound (1e-3) is asserted for the bench encoder
+    print(f"convnext_tiny: max relative embedding error {rel:.2e}")
+    assert rel <= 1e-3, rel  # north_star tolerance (measured 4.1e-4 with the white-centred 4x4-patch rows)
 
 
 def test_convnext_crop_patch4_path_equals_nchw_path():

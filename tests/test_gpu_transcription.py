@@ -72,3 +72,48 @@ def test_transcriptions_identical_to_oracle_and_readable():
     assert np.array_equal(idx[:, 0], ri.numpy()[:, 0])  # top-1 ids identical for every character
     _, cer_gt = textproc.textline_evaluation(pairs_gt, no_spaces_in_eval=True)
     assert cer_gt < 0.15, cer_gt  # the quick-fit recogniser reads the synthetic lines
+
+
+def test_ad_hoc_index_on_device_matches_oracle_index(tmp_path):
+    """SURVEY 8f N2 (`--ad_hoc_index_root_dir`, infer_effocr.py:190-201): a folder of rendered glyphs -> prototypes embedded
+    on the device (fused crop kernel + encoder + L2 norm) -> new index.  Against the oracle's index of the same renders
+    (per-glyph transform -> ViT -> normalise, what InferenceModel.train_knn computes): same characters in the same order,
+    prototypes within the embedding tolerance, and recognition through the new index reads held-out crops like the
+    oracle's index does."""
+    from PIL import Image
+    from effocr_b200 import lineio, synth
+    from effocr_b200.pipeline import RecognizerPipeline
+    from oracle import knn as OK, transform as OT, vit as OV
+    vit_s = GOLDEN.parent / "quickfit_vit_small.npz"  # the full-depth quick-fit ViT-S (tools/quickfit_recognizer.py)
+    if not vit_s.exists():
+        pytest.skip("quick-fit ViT-S weights not generated")
+    sd = {k: torch.from_numpy(v.astype(np.float32)) for k, v in np.load(vit_s).items()}
+    glyphs = synth.ASCII_GLYPHS[:40]
+    renders = {}
+    for ch in glyphs:
+        im, cb, _wb, _c = synth.render_line(ch, font_size=40, x0=6, width=128)
+        crop = np.ascontiguousarray(im[:, int(round(float(cb[0][0]))):int(round(float(cb[0][2]))), :])
+        cls = f"0x{ord(ch):x}"
+        (tmp_path / cls).mkdir()
+        Image.fromarray(crop).save(tmp_path / cls / f"{cls}_NotoSerif-Regular.png")
+        Image.fromarray(crop[:, ::-1]).save(tmp_path / cls / f"{cls}_OtherFont.png")           # another font: ignored
+        Image.fromarray(crop).save(tmp_path / cls / f"PAIRED_{cls}_NotoSerif-Regular_0.png")   # a scanned crop: ignored
+        renders[ch] = crop
+    pipe = RecognizerPipeline(sd, torch.zeros(1, 384), max_batch=16)  # max_batch < 40: chunked index construction
+    chars = lineio.build_ad_hoc_index(str(tmp_path), pipe, lang="en")
+    order = sorted(glyphs, key=lambda c: f"0x{ord(c):x}")  # ImageFolder walks the class directories in sorted order
+    assert chars == order == pipe.candidate_chars and pipe.index.ntotal == 40
+    with torch.no_grad():
+        ref = OV.l2_normalize(OV.vit_forward(sd, torch.from_numpy(np.stack([OT.paired_transform(renders[c]) for c in order]))))
+    got = torch.from_numpy(pipe.index.reconstruct_n())
+    rel = ((got - ref).norm(dim=1) / ref.norm(dim=1)).max().item()
+    print(f"ad-hoc index: max relative prototype error {rel:.2e}")
+    assert rel <= 1e-3, rel
+    crops, labels = synth.synthetic_crops(400, seed=9)
+    keep = [i for i, l in enumerate(labels) if l in order][:128]
+    _d, idx = pipe.recognize_crops([crops[i] for i in keep], k=1)
+    with torch.no_grad():
+        q = OV.l2_normalize(OV.vit_forward(sd, torch.from_numpy(np.stack([OT.paired_transform(crops[i]) for i in keep]))))
+    _rd, ri = OK.flat_ip_search(ref, q, 1)
+    assert np.array_equal(idx[:, 0], ri.numpy()[:, 0])
+    assert np.mean([order[j] == labels[i] for i, j in zip(keep, idx[:, 0])]) > 0.8
