@@ -31,6 +31,7 @@ class EffocrError(RuntimeError):
 # (tests/test_abi.py cross-checks this table against the header and the .so export table).
 SIGNATURES = {
     "effocr_abi_version": (c_int, []),
+    "effocr_build_flags": (c_int, []),
     "effocr_last_error": (C.c_char_p, []),
     "effocr_device_ok": (c_int, []),
     "effocr_launch_count": (c_ll, []),

@@ -56,7 +56,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     def compile_one(job):
         src, obj = job
         # EFFOCR_NVCC_EXTRA: extra nvcc flags for experiments, e.g. "-DEFFOCR_ATT_ABLATION" (tools/att_ablate.py); rebuild with --force
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("EFFOCR_NVCC_EXTRA", "").split(), "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
+        # EFFOCR_AB=1: also compile the A/B kernel variants (earlier attention kernels, direct-store GEMM epilogues, ...)
+        ab = ["-DEFFOCR_AB"] if os.environ.get("EFFOCR_AB") == "1" else []
+        cmd = [nvcc, *NVCC_FLAGS, *ab, *os.environ.get("EFFOCR_NVCC_EXTRA", "").split(), "-I", str(INCLUDE), "-c", str(src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

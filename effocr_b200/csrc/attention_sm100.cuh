@@ -62,6 +62,7 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {
   return make_idesc_f16(M, N) | (1u << 16);
 }
 
+#ifdef EFFOCR_AB  // A/B variants (two-pass / fp16-delta single pass / 16 softmax warps), not part of the product build
 template <bool kSinglePass>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
@@ -708,6 +709,7 @@ attention_tc16_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
 }
 
+#endif  // EFFOCR_AB
 // ------------------------------------------------------------------ one TMEM pass, two key blocks (default)
 // Output tile through TMA (kTmaOut): each softmax warp stages its 32 rows x 64 fp16 in the (dead) first P chunk of its group,
 // SWIZZLE_128B, and one lane issues a 4-D tensor store {64 columns, 32 tokens, 1 image} -- tokens >= 197 are clipped by the
@@ -1085,6 +1087,7 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
 }
 
+#ifdef EFFOCR_AB  // A/B variant, not part of the product build (python -m effocr_b200.build with EFFOCR_AB=1)
 // ------------------------------------------------------------------ one TMEM pass, three key blocks, 16 softmax warps
 // The two-block kernel above is bound by its softmax warps: tools/att_timeline.py shows each of them busy ~5 700 of the
 // 7 300 cycles a (image, head) unit takes (3 900 softmax + 1 800 epilogue), one exponential every 8 cycles per warp being
@@ -1452,4 +1455,5 @@ attention_tc3b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
   if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
 }
 
+#endif  // EFFOCR_AB
 }  // namespace effocr

@@ -7,10 +7,13 @@
 //   block               dwconv7x7 + bias + LayerNorm fused (fp32 in, fp16 out)  ->  GEMM fc1 + bias + GELU (fp16)
 //                       ->  GEMM fc2 + bias, * gamma, TMA reduce-add into x (fp32, in place)
 //   head                global average pool + LayerNorm -> fp32 [B, 768]
+#include <stdlib.h>
+
 #include <vector>
 
 #include "../../include/effocr_b200.h"
 #include "gemm.h"
+#include "mlp.h"
 
 namespace effocr {
 
@@ -190,6 +193,11 @@ __global__ void __launch_bounds__(256) cnx_head_kernel(const float* __restrict__
 struct CnxBlock {
   float *dw_w, *dw_b, *ln_w, *ln_b, *b1, *b2, *gamma;
   __half *w1, *w2;
+  // stages of width 192 / 384 run the pointwise pair through the fused MLP kernel (mlp_sm100.cuh: fc1 + GELU + fc2 +
+  // residual in one kernel, the [M, 4C] hidden activations never reach HBM); the layer scale is folded into fc2:
+  // x += gamma * (P . W2^T + b2) == P . (diag(gamma) W2)^T + gamma * b2
+  __half* w2g = nullptr;
+  float* b2g = nullptr;
 };
 struct CnxStage {
   float *ds_ln_w = nullptr, *ds_ln_b = nullptr, *ds_b = nullptr;
@@ -263,6 +271,10 @@ static int cnx_forward_chunk(CnxHandle* h, int B, float* emb, cudaStream_t s) {
   float* x = h->xa;
   float* xalt = h->xb;
   int H = 56, W = 56;
+  static const bool fused_mlp = [] {
+    const char* e = getenv("EFFOCR_MLP_FUSED");  // "0" = separate fc1 / fc2 GEMMs everywhere (A/B runs)
+    return !(e && e[0] == '0');
+  }();
   for (int st = 0; st < 4; ++st) {
     const int C = kCnxDims[st];
     if (st > 0) {
@@ -290,6 +302,13 @@ static int cnx_forward_chunk(CnxHandle* h, int B, float* emb, cudaStream_t s) {
         default: launch_dwconv<768>(x, k, h->h16, B, H, W, s); break;
       }
       EFFOCR_CUDA(cudaGetLastError());
+      if (k.w2g && fused_mlp) {
+        MlpArgs m;
+        m.h = h->h16; m.ldh = C; m.w1 = k.w1; m.b1 = k.b1; m.w2 = k.w2g; m.b2 = k.b2g;
+        m.x = x; m.ldx = C; m.M = static_cast<int>(M); m.D = C; m.HID = 4 * C;
+        EFFOCR_TRY(mlp_fused_f16(m, s));
+        continue;
+      }
       g = GemmArgs();
       g.A = h->h16; g.lda = C; g.W = k.w1; g.ldw = C; g.M = static_cast<int>(M); g.N = 4 * C; g.K = C;
       g.out = h->mid; g.ldo = 4 * C; g.bias = k.b1; g.act = 1; g.prof_tag = PROF_GEMM_FC1;
@@ -372,6 +391,17 @@ extern "C" int effocr_convnext_create(int max_batch, const float* const* hw, int
         if ((st = h->up16(&k.w2, to16(hw[i], static_cast<size_t>(4) * C * C)))) break; ++i;
         if ((st = h->up32(&k.b2, hw[i], C))) break; ++i;
         if ((st = h->up32(&k.gamma, hw[i], C))) break; ++i;
+        if (mlp_fused_supported(C, 4 * C)) {
+          const float *w2 = hw[i - 3], *b2 = hw[i - 2], *gm = hw[i - 1];
+          std::vector<__half> wg(static_cast<size_t>(4) * C * C);
+          std::vector<float> bg(C);
+          for (int n = 0; n < C; ++n) {
+            bg[n] = gm[n] * b2[n];
+            for (int c = 0; c < 4 * C; ++c) wg[static_cast<size_t>(n) * 4 * C + c] = __float2half_rn(gm[n] * w2[static_cast<size_t>(n) * 4 * C + c]);
+          }
+          if ((st = h->up16(&k.w2g, wg))) break;
+          if ((st = h->up32(&k.b2g, bg.data(), C))) break;
+        }
         S.blocks.push_back(k);
       }
     }

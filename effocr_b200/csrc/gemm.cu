@@ -55,6 +55,7 @@ static int launch_bn(int bn, const GemmArgs& a, const typename Epi::Params& ep, 
   return fail(EFFOCR_ERR_INVALID, "block_n must be 64, 128, 192 or 256");
 }
 
+#ifdef EFFOCR_AB
 template <int ACT, typename OutT, bool RES>
 static int launch_store(int bn, const GemmArgs& a, cudaStream_t stream) {
   using Epi = EpiStore<ACT, OutT, RES>;
@@ -67,6 +68,7 @@ static int launch_store(int bn, const GemmArgs& a, cudaStream_t stream) {
   ep.ldr = a.ldr;
   return launch_bn<Epi>(bn, a, ep, stream);
 }
+#endif
 
 // ---- TMA-store / TMA-reduce epilogue path (aligned outputs, no separate residual buffer)
 template <int BN, int ACT, bool F32, bool RED>
@@ -235,6 +237,11 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
     ep.patches = a.patches;
     return launch_bn<EpiPatchEmbed>(bn, a, ep, stream);
   }
+#ifndef EFFOCR_AB
+  // every product GEMM takes the TMA-store / TMA-reduce epilogue above or the patch-embed epilogue; the generic
+  // direct-store epilogues (separate residual buffer, forced `epilogue = 1`) exist in A/B builds only
+  return fail(EFFOCR_ERR_INVALID, "gemm: this shape needs the direct-store epilogue, which is compiled out of this build (EFFOCR_AB=1)");
+#else
   const bool res = a.resid != nullptr;
   if (a.out_f32) {
     if (a.act != ACT_NONE) return fail(EFFOCR_ERR_INVALID, "gemm: fp32 output supports act=none only");
@@ -252,6 +259,7 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
                  : launch_store<ACT_SILU, __half, false>(bn, a, stream);
   }
   return fail(EFFOCR_ERR_INVALID, "gemm: unsupported activation / residual combination");
+#endif
 }
 
 }  // namespace effocr

@@ -192,6 +192,14 @@ static const char* kProfNames[PROF_NUM_TAGS] = {
 
 }  // namespace effocr
 
+extern "C" int effocr_build_flags() {
+#ifdef EFFOCR_AB
+  return 1;
+#else
+  return 0;
+#endif
+}
+
 extern "C" long long effocr_launch_count(void) { return effocr::g_launches.load(); }
 extern "C" void effocr_profile_enable(int on) {
   effocr::prof_drain();

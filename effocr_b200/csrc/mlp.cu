@@ -76,6 +76,7 @@ int mlp_fused_f16(const MlpArgs& a, cudaStream_t stream) {
     const char* e = getenv("EFFOCR_MLP_CHUNK");  // A/B: 64 = the first schedule (N = 64 fc1 MMAs, two S buffers), 128 (default)
     return e ? atoi(e) : 128;
   }();
+#ifdef EFFOCR_AB  // the 64-wide schedule at D = 384, the one-chunk look-ahead and the clock64 timeline are A/B-only
   if (chunk == 128 && a.D == 384 && !a.dbg) return launch_mlp128<384>(a, stream);
   static const int ahead = [] {
     const char* e = getenv("EFFOCR_MLP_AHEAD");  // A/B: 1 = fc1 one chunk ahead of fc2, 2 (default) = two chunks
@@ -83,6 +84,11 @@ int mlp_fused_f16(const MlpArgs& a, cudaStream_t stream) {
   }();
   if (ahead == 1) return a.D == 192 ? launch_mlp<192, 1>(a, stream) : launch_mlp<384, 1>(a, stream);
   return a.D == 192 ? launch_mlp<192, 2>(a, stream) : launch_mlp<384, 2>(a, stream);
+#else
+  (void)chunk;
+  if (a.dbg) return fail(EFFOCR_ERR_INVALID, "mlp_fused: the timeline variant is compiled out of this build (EFFOCR_AB=1)");
+  return a.D == 384 ? launch_mlp128<384>(a, stream) : launch_mlp<192, 2>(a, stream);
+#endif
 }
 
 }  // namespace effocr

@@ -92,6 +92,7 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
 int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
+#ifdef EFFOCR_AB
   if (impl == 1) {
     static bool attr = false;
     if (!attr) {
@@ -100,17 +101,23 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     }
     KernelScope ks(PROF_ATTENTION, s);
     attention_197x64_kernel<<<batch * H, kAttnThreads, kAttnSmemBytes, s>>>(qkv, out, T, H, scale_log2e);
-  } else {
+  } else
+#else
+  if (impl != 0) return fail(EFFOCR_ERR_INVALID, "attention: A/B variants are compiled out of this build (EFFOCR_AB=1 python -m effocr_b200.build --force)");
+#endif
+  {
     static bool attr = false;
     if (!attr) {
+#ifdef EFFOCR_AB
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt16SmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
+      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
+#endif
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
       EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
-      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
-      EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc3b_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAt3SmemBytes));
       attr = true;
     }
     static const int env_variant = [] {
@@ -118,11 +125,15 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
       return e ? atoi(e) : 0;
     }();
     int variant = 0;  // 0: one TMEM pass / two key blocks, 1: single pass via fp16 deltas, 2: two passes, 4: 16 warps two passes
+#ifdef EFFOCR_AB
     if (impl == 2) variant = 2;
     else if (impl == 3) variant = 1;
     else if (impl == 4) variant = 4;
     else if (impl == 5) variant = 5;
     else if (env_variant == 1 || env_variant == 2 || env_variant == 4 || env_variant == 5) variant = env_variant;
+#else
+    (void)env_variant;
+#endif
     const long long rows = static_cast<long long>(batch) * T;
     const int D = H * 64;
     CUtensorMap tq, tkv;
@@ -131,6 +142,7 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
     const int pairs = batch * H;
     const int grid = pairs < sm_count() ? pairs : sm_count();
     KernelScope ks(PROF_ATTENTION, s);
+#ifdef EFFOCR_AB
     if (variant == 1) attention_tc_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
     else if (variant == 2) attention_tc_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
     else if (variant == 4) attention_tc16_kernel<<<grid, kAt16Threads, kAt16SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e);
@@ -139,7 +151,9 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
       long long* dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
       if (dbg) attention_tc3b_kernel<true><<<grid, kAt3Threads, kAt3SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, dbg);
       else attention_tc3b_kernel<false><<<grid, kAt3Threads, kAt3SmemBytes, s>>>(tq, tkv, out, batch, H, scale_log2e, nullptr);
-    } else {
+    } else
+#endif
+    {
       const char* e = getenv("EFFOCR_ATT_DBG_PTR");  // tools/att_timeline.py: device buffer of 32 int64 receiving wait-time totals
       long long* dbg = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
       // output tile as a 4-D tensor {D, 197 tokens, batch, 1}: a 32-token box that runs past token 196 is clipped

@@ -193,6 +193,7 @@ __global__ void cls_pos_kernel(float* __restrict__ x, const float* __restrict__ 
   x[static_cast<long long>(b) * T * D + c] = cls[c] + pos[c];
 }
 
+#ifdef EFFOCR_AB  // first-generation mma.sync attention kernel: A/B only
 // ------------------------------------------------------------------ fused attention, 197 tokens, head dim 64
 // One CTA per (image, head).  Q, K, V ([T, 64] fp16 each) are staged in shared memory; each
 // warp owns 16-row stripes of the score matrix, keeps the whole 16 x 208 stripe in registers
@@ -338,5 +339,7 @@ attention_197x64_kernel(const __half* __restrict__ qkv, __half* __restrict__ out
     }
   }
 }
+
+#endif  // EFFOCR_AB
 
 }  // namespace effocr

@@ -22,6 +22,7 @@
 
 namespace effocr {
 
+#ifdef EFFOCR_AB
 // ------------------------------------------------------------------ gather kernels (HBM-bound)
 // layer 0: f32 NCHW image -> im2col rows of Conv(3, 32, k6, s2, p2); col = c*36 + ky*6 + kx (torch
 // weight order), zero-padded from 108 to 112 columns.
@@ -51,6 +52,8 @@ __global__ void __launch_bounds__(256) yolo_im2col0_kernel(const float* __restri
     *reinterpret_cast<uint4*>(col + row * 112 + vec * 8) = *reinterpret_cast<const uint4*>(v);
   }
 }
+
+#endif  // EFFOCR_AB
 
 // ------------------------------------------------------------------ layer 0 as an implicit GEMM (no im2col buffer)
 // Conv(3, 32, k6, s2, p2) + folded BN + SiLU straight from the f32 NCHW image to the fp16 NHWC activation.  With K = 108
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(256) yolo_stem_kernel(const float* __restrict_
   }
 }
 
+#ifdef EFFOCR_AB
 // 3x3, pad 1, stride s: NHWC fp16 (pixel pitch ld_in) -> [B*Ho*Wo, 9*C], column = (ky*3 + kx)*C + c.
 // One 16-byte vector per thread; C / 8 is a power of two and the index fits 32 bits (host checks), so the index
 // arithmetic is shifts, one constant division and two 32-bit divisions -- the first version's 64-bit runtime
@@ -217,6 +221,8 @@ __global__ void __launch_bounds__(256) yolo_im2col3_kernel(const __half* __restr
     *reinterpret_cast<uint4*>(col + static_cast<long long>(row) * (9u * C) + tap * C + cv * 8) = v;
   }
 }
+
+#endif  // EFFOCR_AB
 
 // nearest 2x upsample into a channel slice of the consumer's concat buffer
 __global__ void __launch_bounds__(256) yolo_upsample2x_kernel(const __half* __restrict__ in, int ld_in,
@@ -521,10 +527,14 @@ struct YoloRun {
     if (status) return;
     const int Ho = (H - 1) / cw.s + 1, Wo = (W - 1) / cw.s + 1;
     const long long rows = static_cast<long long>(B) * Ho * Wo;
+#ifdef EFFOCR_AB
     static const bool use_im2col = [] {
       const char* e = getenv("EFFOCR_YOLO_CONV3");  // "im2col" = explicit gather + GEMM (first version; A/B runs)
       return e && e[0] == 'i';
     }();
+#else
+    constexpr bool use_im2col = false;
+#endif
     if (split()) {
       const __half* rp = resid ? resid->p : nullptr;
       const int rl = resid ? resid->ld : 0;
@@ -544,6 +554,7 @@ struct YoloRun {
       else status = launch_conv3<256, 64>(in.p, in.ld, B, H, W, cw.cin, cw.w, cw.kdim, cw.b, cw.cout, cw.s, out.p, out.ld, rp, rl, s);
       return;
     }
+#ifdef EFFOCR_AB
     if (static_cast<size_t>(rows) * cw.kdim > h->col_elems) { status = fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small"); return; }
     {
       KernelScope ks(PROF_CONV_IM2COL, s);
@@ -560,6 +571,7 @@ struct YoloRun {
       }
     }
     gemm(h->col, cw.kdim, rows, cw, out, resid);
+#endif
   }
   // C3(c1, c2, n, shortcut) at a level with `pix` pixels of size Hl x Wl
   void c3(Act in, int c2, int n, bool shortcut, int Hl, int Wl, Act out) {
@@ -605,10 +617,14 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
   // layer 0
   {
     const ConvW& cw = h->convs[r.conv_i++];
+#ifdef EFFOCR_AB
     static const bool stem_gemm = [] {
       const char* e = getenv("EFFOCR_YOLO_STEM");  // "gemm" = explicit im2col + tcgen05 GEMM (first version; A/B runs)
       return e && e[0] == 'g';
     }();
+#else
+    constexpr bool stem_gemm = false;
+#endif
     if (r.split()) {
       const int tiles = B * ((H1 + kStemF32TH - 1) / kStemF32TH) * ((W1 + kStemF32TW - 1) / kStemF32TW);
       const int grid = tiles < 4 * sm_count() ? tiles : 4 * sm_count();
@@ -616,12 +632,14 @@ static int yolo_forward_impl(YoloHandle* h, const float* img, int B, int H, int 
       yolo_stem_f32_kernel<<<grid, 256, 0, s>>>(img, cw.wf, cw.b, x0.p, x0.p + h->lo_off, x0.ld, B, H, W);
       EFFOCR_CUDA(cudaGetLastError());
     } else if (stem_gemm) {
+#ifdef EFFOCR_AB
       if (static_cast<size_t>(p1) * 112 > h->col_elems) return fail(EFFOCR_ERR_NOMEM, "yolo: im2col scratch too small");
       {
         KernelScope ks(PROF_CONV_IM2COL, s);
         yolo_im2col0_kernel<<<grid_for(p1 * 14), 256, 0, s>>>(img, h->col, B, H, W);
       }
       r.gemm(h->col, 112, p1, cw, x0, nullptr);
+#endif
     } else {
       const int tiles = B * ((H1 + kStemTH - 1) / kStemTH) * ((W1 + kStemTW - 1) / kStemTW);
       const int grid = tiles < sm_count() ? tiles : sm_count();  // persistent, one CTA per SM (222 registers: B fragments + prefetch)

@@ -41,6 +41,9 @@ extern "C" {
 
 /* ---- library ---------------------------------------------------------------------------- */
 EFFOCR_API int effocr_abi_version(void);
+/* bit 0: the library was built with -DEFFOCR_AB (A/B kernel variants kept for experiments: earlier attention kernels, the
+ * 64-wide fused-MLP schedule at D = 384, direct-store GEMM epilogues, im2col convolutions).  The product build is 0. */
+EFFOCR_API int effocr_build_flags(void);
 EFFOCR_API const char* effocr_last_error(void);
 /* 0 when the current CUDA device is an sm_100 part, EFFOCR_ERR_NO_DEVICE / _CUDA otherwise. */
 EFFOCR_API int effocr_device_ok(void);
