@@ -65,6 +65,10 @@ def parse():
     ap.add_argument("--paths-lines", type=int, default=2048,
                     help="line FILES per GPU for the path-driver measurement (config C5's mechanism: PNGs on disk -> "
                          "lineio.run_effocr_paths_sharded); 0 = skip")
+    ap.add_argument("--font-dir", default=None,
+                    help="render the synthetic lines / crops with the TTF files below this directory (e.g. the reference's "
+                         "english_font_files/) instead of Pillow's bundled default font; the quick-fit weights were fitted on the "
+                         "default font, so the id-identity gates then apply to decidable characters only")
     ap.add_argument("--index-random", action="store_true",
                     help="profiling runs: random unit-norm prototypes instead of embedding rendered glyphs")
     return ap.parse_args()
@@ -573,6 +577,12 @@ def main():
     except Exception:
         pass
 
+    fonts = "Pillow's bundled scalable default font (the reference's english_font_files/ are not part of this repository; --font-dir selects them)"
+    if args.font_dir:
+        nf = synth.set_font_dir(args.font_dir)
+        if nf == 0:
+            raise SystemExit(f"--font-dir {args.font_dir}: no TTF / OTF files found")
+        fonts = f"{nf} font files from {args.font_dir}, round-robin per line"
     B, K = args.batch, args.k
     sd, weights_desc = encoder_state(0)
     D, mlp = 384, 1536
@@ -797,7 +807,8 @@ def main():
             decidable = margin > 4 * max(rel, 1e-3)  # SURVEY.md 8c rule 3: 4 x the embedding tolerance
             agree = (idx_gpu[:, 0] == idx_ref[:, 0])
             trained = weights_desc.startswith("quick-fit")
-            parity_ok = rel <= 1e-3 and (not trained or (float(decidable.float().mean()) >= 0.95 and bool(agree[decidable].all())))
+            strict = trained and not args.font_dir  # foreign fonts: the quick-fit margins are not guaranteed, ids are compared where decidable
+            parity_ok = rel <= 1e-3 and bool(agree[decidable].all()) and (not strict or float(decidable.float().mean()) >= 0.95)
             cpu_block = {"value": ncpu / dt, "unit": "crops/s", "cores": cores, "kind": "port",
                          "sample": f"first {ncpu} crops of the same batch, torch fp32 on {cores} host threads, "
                                    "oracle port (timm/faiss/onnxruntime are not installable here)",
@@ -812,7 +823,7 @@ def main():
             "metric": "char-crops/sec recognizer+kNN (crop transform + ViT-S/16 + kNN)",
             "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "numerics": "f16 operands, f32 accumulate / residual stream / LayerNorm / softmax", "data": f"synthetic (Pillow-rendered glyph crops; {weights_desc})",
+            "dtype": "f16", "numerics": "f16 operands, f32 accumulate / residual stream / LayerNorm / softmax", "data": f"synthetic (rendered glyph crops, {fonts}; {weights_desc})",
             "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": packed.h2d_bytes, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

@@ -42,6 +42,8 @@ SIGNATURES = {
     "effocr_profile_read": (c_int, [c_int, c_void_p, c_void_p]),
     "effocr_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
+    "effocr_ln_gemm_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
+                                   c_int, c_void_p]),
     "effocr_mlp_fused_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
                                      c_int, c_void_p]),
     "effocr_proj_ln_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p,

@@ -3,6 +3,7 @@
 #include "../../include/effocr_b200.h"
 #include "gemm_sm100.cuh"
 #include "gemm_sm100_tma_epi.cuh"
+#include "lnqkv_sm100.cuh"
 
 namespace effocr {
 
@@ -209,6 +210,41 @@ static int try_gemm_tma(int bn, const GemmArgs& a, cudaStream_t stream) {
   return -1;
 }
 
+bool ln_gemm_supported(int D, int N) { return D == kLnqD && N % 8 == 0 && N >= 192; }
+
+// out[M, N] (fp16) = (LayerNorm(x[M, 384]) * gamma + beta) . W[N, 384]^T + bias  -- one kernel (lnqkv_sm100.cuh)
+int ln_gemm_f16(const LnGemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0) return EFFOCR_OK;
+  if (!ln_gemm_supported(a.D, a.N)) return fail(EFFOCR_ERR_INVALID, "ln_gemm: width must be 384 and N a multiple of 8, >= 192");
+  if (!a.x || !a.gamma || !a.beta || !a.W || !a.out) return fail(EFFOCR_ERR_INVALID, "ln_gemm: null operand");
+  if (a.ldx % 4 != 0 || (reinterpret_cast<uintptr_t>(a.x) & 15) || (reinterpret_cast<uintptr_t>(a.gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(a.beta) & 15) || (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) || a.ldo % 8 != 0 ||
+      (reinterpret_cast<uintptr_t>(a.out) & 15) || a.ldw % 8 != 0)
+    return fail(EFFOCR_ERR_INVALID, "ln_gemm: operands must be 16-byte aligned with 16-byte multiple pitches");
+  constexpr int BN = 192;
+  using Cfg = LnQkvCfg<BN>;
+  CUtensorMap tb, tc;
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, kLnqD, a.ldw, BN));
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, 2, a.M, a.N, a.ldo, 32, 32, 64));
+  auto kern = ln_gemm_astat_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  const int num_m = (a.M + kBlockM - 1) / kBlockM;
+  const int grid = num_m < sm_count() ? num_m : sm_count();
+  EpiTmaParams ep;
+  ep.bias = a.bias;
+  ep.gamma = nullptr;
+  {
+    KernelScope ks(a.prof_tag, stream);
+    kern<<<grid, kLnqThreads, Cfg::kSmemBytes, stream>>>(a.x, a.ldx, a.gamma, a.beta, a.eps, tb, tc, a.M, a.N, ep);
+  }
+  EFFOCR_CUDA(cudaGetLastError());
+  return EFFOCR_OK;
+}
+
 int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return fail(EFFOCR_ERR_INVALID, "gemm: empty problem");
   if (!a.A || !a.W || !a.out) return fail(EFFOCR_ERR_INVALID, "gemm: null operand");
@@ -263,6 +299,17 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace effocr
+
+extern "C" int effocr_ln_gemm_f16(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta, float eps,
+                                  const void* d_w, long long ldw, const float* d_bias, void* d_out, long long ldo, int M, int N,
+                                  int D, void* stream) {
+  EFFOCR_TRY(effocr::require_sm100());
+  effocr::LnGemmArgs a;
+  a.x = d_x; a.ldx = ldx; a.gamma = d_gamma; a.beta = d_beta; a.eps = eps;
+  a.W = reinterpret_cast<const __half*>(d_w); a.ldw = ldw; a.bias = d_bias;
+  a.out = reinterpret_cast<__half*>(d_out); a.ldo = ldo; a.M = M; a.N = N; a.D = D;
+  return effocr::ln_gemm_f16(a, reinterpret_cast<cudaStream_t>(stream));
+}
 
 extern "C" int effocr_gemm_f16(const void* A, long long lda, const void* W, long long ldw, int M, int N, int K,
                                const float* bias, const float* gamma, const void* resid, long long ldr, void* out,

@@ -28,6 +28,23 @@ struct GemmArgs {
 };
 
 int gemm_f16(const GemmArgs& a, cudaStream_t stream);
+
+struct LnGemmArgs {
+  const float* x = nullptr;  // [M, D] fp32 residual stream, row pitch ldx
+  long long ldx = 0;
+  const float *gamma = nullptr, *beta = nullptr;  // LayerNorm affine [D]
+  float eps = 1e-6f;
+  const __half* W = nullptr;  // [N, D] (torch Linear layout), row pitch ldw
+  long long ldw = 0;
+  const float* bias = nullptr;  // [N] or null
+  __half* out = nullptr;        // [M, N] fp16, row pitch ldo
+  long long ldo = 0;
+  int M = 0, N = 0, D = 0;
+  int prof_tag = PROF_GEMM_QKV;
+};
+bool ln_gemm_supported(int D, int N);
+// out = (LayerNorm(x) * gamma + beta) . W^T + bias in one kernel: the normalised operand never reaches HBM
+int ln_gemm_f16(const LnGemmArgs& a, cudaStream_t stream);
 int choose_block_n(int N);
 
 }  // namespace effocr

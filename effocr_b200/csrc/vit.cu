@@ -220,8 +220,23 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     const char* e = getenv("EFFOCR_VIT_LAST_BLOCK_FULL");  // "1" = run the last block on all 197 tokens (A/B runs)
     return !(e && e[0] == '1');
   }();
+  // norm1 + QKV in one kernel (lnqkv_sm100.cuh) is bit-identical to the two-kernel path but measured SLOWER (267 us vs
+  // 71 + 176 us stand-alone at batch 1024: eight LayerNorm warps per SM cannot keep enough of x in flight); it stays an
+  // opt-in experiment: EFFOCR_LN_QKV=1
+  static const bool lnq_env = [] {
+    const char* e = getenv("EFFOCR_LN_QKV");
+    return e && e[0] == '1';
+  }();
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
+    const bool last_cls = cls_env && l == v->depth - 1;
+    if (lnq_env && !last_cls && ln_gemm_supported(D, 3 * D)) {
+      // norm1 + QKV projection in one kernel: the normalised fp16 operand is produced on the SM (lnqkv_sm100.cuh)
+      LnGemmArgs q;
+      q.x = v->x; q.ldx = D; q.gamma = L.ln1_w; q.beta = L.ln1_b; q.eps = v->eps; q.W = L.w_qkv; q.ldw = D; q.bias = L.b_qkv;
+      q.out = v->qkv; q.ldo = 3 * D; q.M = M; q.N = 3 * D; q.D = D; q.prof_tag = PROF_GEMM_QKV;
+      EFFOCR_TRY(ln_gemm_f16(q, s));
+    } else {
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
     if (cls_env && l == v->depth - 1) {
       // last block: K and V for every token, Q for the class tokens only (see below)
@@ -238,6 +253,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
       g.A = v->h16; g.lda = D; g.W = L.w_qkv; g.ldw = D; g.M = M; g.N = 3 * D; g.K = D;
       g.out = v->qkv; g.ldo = 3 * D; g.bias = L.b_qkv; g.prof_tag = PROF_GEMM_QKV;
       EFFOCR_TRY(gemm_f16(g, s));
+    }
     }
     // Last block: only the class token reaches the embedding (timm pools x[:, 0]), so the rows of the 196 patch tokens
     // are dead after K and V have been formed: CLS-query attention, then projection / norm2 / MLP on the B class rows

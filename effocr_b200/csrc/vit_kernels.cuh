@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ln_math.cuh"
+
 namespace effocr {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -43,11 +45,11 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < ITERS * VEC; ++i) s += v[i];
-  const float mean = warp_sum(s) * (1.0f / D);
+  const float mean = __fmul_rn(warp_sum(s), 1.0f / D);
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < ITERS * VEC; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
-  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+  for (int i = 0; i < ITERS * VEC; ++i) { const float d = __fsub_rn(v[i], mean); q = __fmaf_rn(d, d, q); }
+  const float rstd = ln_rstd(warp_sum(q), 1.0f / D, eps);
   OutT* orow = out + static_cast<long long>(row) * ldo;
 #pragma unroll
   for (int j = 0; j < ITERS; ++j) {
@@ -55,10 +57,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
       const int c = (j * 32 + lane) * 4;
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      const float y0 = (v[j * 4] - mean) * rstd * g.x + b.x;
-      const float y1 = (v[j * 4 + 1] - mean) * rstd * g.y + b.y;
-      const float y2 = (v[j * 4 + 2] - mean) * rstd * g.z + b.z;
-      const float y3 = (v[j * 4 + 3] - mean) * rstd * g.w + b.w;
+      const float y0 = ln_affine(v[j * 4], mean, rstd, g.x, b.x);
+      const float y1 = ln_affine(v[j * 4 + 1], mean, rstd, g.y, b.y);
+      const float y2 = ln_affine(v[j * 4 + 2], mean, rstd, g.z, b.z);
+      const float y3 = ln_affine(v[j * 4 + 3], mean, rstd, g.w, b.w);
       if constexpr (sizeof(OutT) == 2) {
         uint2 pk;
         *reinterpret_cast<__half2*>(&pk.x) = __floats2half2_rn(y0, y1);
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __rest
       }
     } else {
       const int c = j * 32 + lane;
-      const float y = (v[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      const float y = ln_affine(v[j], mean, rstd, __ldg(gamma + c), __ldg(beta + c));
       if constexpr (sizeof(OutT) == 2) orow[c] = __float2half_rn(y);
       else orow[c] = y;
     }

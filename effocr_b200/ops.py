@@ -49,6 +49,23 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias=None, act: int = ACT_NONE, out_d
     return out
 
 
+def ln_gemm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, w: torch.Tensor, bias=None, eps: float = 1e-6,
+            out=None) -> torch.Tensor:
+    """(LayerNorm(x) * gamma + beta) @ w.T + bias -> fp16, one fused tcgen05 kernel (x fp32 [M, 384], w fp16 [N, 384])."""
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x")
+    w = _cuda(w, torch.float16, "w")
+    M, D = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == D and x.stride(1) == 1 and w.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=torch.float16)
+    _lib.check(lib.effocr_ln_gemm_f16(x.data_ptr(), x.stride(0), _cuda(gamma, torch.float32, "gamma").data_ptr(),
+                                      _cuda(beta, torch.float32, "beta").data_ptr(), float(eps), w.data_ptr(), w.stride(0),
+                                      _lib.ptr(bias), out.data_ptr(), out.stride(0), M, N, D, _lib.stream_ptr()), "effocr_ln_gemm_f16")
+    return out
+
+
 def mlp_fused(x: torch.Tensor, h: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor,
               b2: torch.Tensor) -> torch.Tensor:
     """x += GELU(h @ w1.T + b1) @ w2.T + b2 in place (fp32 residual x, fp16 h / weights); one fused tcgen05 kernel."""

@@ -10,19 +10,45 @@ import numpy as np
 ASCII_GLYPHS = [chr(c) for c in range(33, 127)]  # the "94-glyph" printable-ASCII charset of BASELINE.json
 
 
-def _font(size: int):
+_FONT_FILES: list = []   # set_font_dir(): TTF/OTF files used round-robin instead of Pillow's default font
+_font_cache: dict = {}
+
+
+def set_font_dir(path) -> int:
+    """Render with the TTF / OTF files below `path` (e.g. the reference's english_font_files/, round-robin per line, as
+    SURVEY.md section 8d describes) instead of Pillow's bundled default font.  `None` restores the default.  Returns the
+    number of font files found.  The committed golden fixtures and quick-fit weights were made with the DEFAULT font:
+    tests never call this; bench.py does when --font-dir is given and says so in its `data` field."""
+    import glob
+    import os
+
+    _FONT_FILES.clear()
+    _font_cache.clear()
+    if path:
+        for ext in ("*.ttf", "*.otf", "*.TTF", "*.OTF"):
+            _FONT_FILES.extend(sorted(glob.glob(os.path.join(str(path), "**", ext), recursive=True)))
+    return len(_FONT_FILES)
+
+
+def _font(size: int, which: int = 0):
     from PIL import ImageFont
 
+    if _FONT_FILES:
+        key = (_FONT_FILES[which % len(_FONT_FILES)], size)
+        if key not in _font_cache:
+            _font_cache[key] = ImageFont.truetype(key[0], size=size)
+        return _font_cache[key]
     return ImageFont.load_default(size=size)
 
 
-def render_line(text: str, height: int = 64, width: int = 1024, font_size: int = 40, x0: int = 6, tracking: float = 0.0):
+def render_line(text: str, height: int = 64, width: int = 1024, font_size: int = 40, x0: int = 6, tracking: float = 0.0,
+                font_index: int = 0):
     """-> (u8 [height, width, 3] RGB, char_boxes [n,4] float32 xyxy, word_boxes [m,4], chars list).
     `tracking`: extra pixels between consecutive glyphs (letter-spacing).  The reference's localizer runs its NMS at
     IoU 0.01 (infer_effocr_onnx_multi.py:441), which only keeps neighbouring characters whose boxes do not touch."""
     from PIL import Image, ImageDraw
 
-    font = _font(font_size)
+    font = _font(font_size, font_index)
     img = Image.new("RGB", (width, height), (255, 255, 255))
     draw = ImageDraw.Draw(img)
     x = float(x0)
@@ -64,9 +90,9 @@ def synthetic_lines(n: int, seed: int = 0, height: int = 64, width: int = 1024, 
     """n rendered lines, 20-40 glyphs each (fewer if the line fills up)."""
     rng = np.random.default_rng(seed)
     out = []
-    for _ in range(n):
+    for i in range(n):
         text = random_text(rng, int(rng.integers(20, 41)))
-        out.append(render_line(text, height, width, font_size=int(rng.integers(34, 44)), tracking=tracking))
+        out.append(render_line(text, height, width, font_size=int(rng.integers(34, 44)), tracking=tracking, font_index=i))
     return out
 
 

@@ -177,6 +177,11 @@ EFFOCR_API int effocr_convnext_forward(effocr_convnext_t h, const void* d_input,
                                        void* stream);
 
 /* building blocks of the encoder, exported for the parity tests */
+/* out fp16 [M, N] = (LayerNorm(x fp32 [M, 384]) * gamma + beta) . W[N, 384]^T + bias: timm Block's attn.qkv(norm1(x)) in one
+ * kernel -- the normalised operand is produced on the SM and never reaches HBM.  D must be 384 (ViT-S). */
+EFFOCR_API int effocr_ln_gemm_f16(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta, float eps,
+                                  const void* d_w, long long ldw, const float* d_bias, void* d_out, long long ldo, int M,
+                                  int N, int D, void* stream);
 EFFOCR_API int effocr_layernorm(const float* d_x, long long ldx, const float* d_gamma, const float* d_beta,
                                 void* d_out, long long ldo, int rows, int dim, float eps, int out_f32, void* stream);
 /* qkv fp16 [B*197, 3*H*64] (rows [q|k|v], each [H,64]) -> out fp16 [B*197, H*64].

@@ -85,6 +85,27 @@ def test_gemm_inplace_residual(M, N, K, gamma, direct):
     assert _rel(x, ref) < (2e-6 if K <= 1536 else 5e-6)  # fp32 accumulation-order noise grows with K
 
 
+@pytest.mark.parametrize("M,N", [(100, 1152), (128, 1152), (1000, 1152), (40000, 1152), (201728 // 4, 1152), (3000, 768), (777, 200)])
+def test_ln_gemm_equals_layernorm_then_gemm(M, N):
+    """norm1 + QKV in one kernel: the A operand is normalised on the SM with the arithmetic of the stand-alone LayerNorm
+    kernel, so the result equals layernorm -> gemm bit for bit (same fp16 operand, same MMA order per tile); row tails,
+    one .. many row blocks per CTA (phase wrap of the A barriers), ragged N."""
+    from effocr_b200 import ops
+    torch.manual_seed(3)
+    D = 384
+    x = torch.randn(M, D, device="cuda") * 2 + 0.5
+    g = torch.randn(D, device="cuda")
+    b = torch.randn(D, device="cuda")
+    w = (torch.randn(N, D, device="cuda") * 0.05).half()
+    bias = torch.randn(N, device="cuda")
+    out = ops.ln_gemm(x, g, b, w, bias)
+    h = ops.layernorm(x, g, b, 1e-6, torch.float16)
+    ref = ops.gemm(h, w, bias=bias)
+    assert _rel(out, ref) < 1e-6
+    ref32 = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6) @ w.float().t() + bias
+    assert _rel(out, ref32) < 6e-4
+
+
 @pytest.mark.parametrize("dim", [96, 192, 384, 768])
 @pytest.mark.parametrize("f32", [False, True])
 def test_layernorm(dim, f32):

@@ -5,7 +5,7 @@ import sys
 sys.path.insert(0, ".")
 import torch
 from effocr_b200 import ops
-which = set(sys.argv[1:]) or {"ln", "qkv", "attention", "proj_ln", "mlp"}
+which = set(sys.argv[1:]) or {"ln", "qkv", "ln_qkv", "attention", "proj_ln", "mlp"}
 B, T, D, HID = 1024, 197, 384, 1536
 M = B * T
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -24,6 +24,7 @@ qout = torch.empty(M, 3 * D, device="cuda", dtype=torch.float16)
 fns = {
     "ln": lambda: ops.layernorm(x, gam, bet),
     "qkv": lambda: ops.gemm(h, wqkv, bias=bq, out=qout),
+    "ln_qkv": lambda: ops.ln_gemm(x, gam, bet, wqkv, bq, out=qout),
     "attention": lambda: ops.attention(qkv, B, 6),
     "proj_ln": lambda: ops.proj_ln(x, att, wproj, bp, gam, bet, out=hout),
     "mlp": lambda: ops.mlp_fused(x, h, w1, b1, w2, b2),

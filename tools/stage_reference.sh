@@ -12,4 +12,5 @@ for d in utils models onnx_engines effocr_datasets; do
   mkdir -p "$DST/$d"
   cp "$SRC/$d"/*.py "$DST/$d"/
 done
+if [ -d "$SRC/english_font_files" ]; then cp -r "$SRC/english_font_files" "$DST"/; fi  # for bench.py --font-dir (2 MB)
 echo "staged $(find "$DST" -name '*.py' | wc -l) files under $DST"
