@@ -289,7 +289,12 @@ def time_pipeline_c3(args, rec_pipe, rank, world, barrier, index_vectors):
         loc._conf_thresh = conf = hi
         weights = "random-init YOLOv5s, confidence threshold calibrated to ~32 character boxes per line"
     chars = [chr(33 + i % 94) for i in range(rec_pipe.index.ntotal)]
-    full = EffOCRPipeline(loc, rec_pipe, chars, lang="en", knn=1)
+    # 64 lines carry ~1 700 characters: an encoder workspace for 2 048 crops takes them in ONE pass (1 024 + 676 would leave
+    # the second pass's last wave of 256-row tiles 12 % empty)
+    from effocr_b200.pipeline import RecognizerPipeline
+
+    rec_c3 = RecognizerPipeline(rec_pipe._state_for_oracle, rec_pipe.index, max_batch=2048)
+    full = EffOCRPipeline(loc, rec_c3, chars, lang="en", knn=1)
     run_effocr(lines[:2 * bl], full, batch_lines=bl)  # warm-up, through the overlapped two-batch path
     overlap = os.environ.get("EFFOCR_PIPELINE_OVERLAP", "1") != "0"  # A/B switch for the two-stream software pipeline
     # wall clock over host + device work: three passes over the same lines, the median is reported (a single host hiccup --

@@ -110,7 +110,9 @@ class EffOCRPipeline:
             buf = self._letterbox_buf = torch.empty((len(images_rgb), 3, shape[0], shape[1]), device="cuda", dtype=torch.float32)
         x = ops.letterbox_resize(packed[0], packed[1], [im.shape[:2] for im in images_rgb], shape[0], shape[1], out=buf)
         out, cnt = self.localizer.run_device(x)
-        out, cnt = out.cpu(), cnt.cpu().tolist()
+        cnt = cnt.cpu().tolist()  # (synchronises) survivors per line: a few dozen of the max_det = 1000 rows
+        top = max(cnt) if cnt else 0
+        out = out[:, :max(top, 1)].cpu()  # only the occupied rows cross PCIe: ~60 KB instead of 1.5 MB per 64 lines
         return [out[i, :cnt[i]] for i in range(len(images_rgb))]
 
     # -- host logic between the two GPU phases (reference semantics, ONNX path)

@@ -17,11 +17,15 @@ from collections import OrderedDict
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-G, P = ROOT / "gpurun_out", ROOT / "profiles"
+G = ROOT / "gpurun_out"
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+# optional second argument: output directory (on the GPU box: gpurun_out/profiles, because the .ncu-rep files are too
+# large to travel back -- the summaries are made there and the reports deleted)
+P = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "profiles"
+P.mkdir(parents=True, exist_ok=True)
 
 for src, dst in (("bench.json", f"{tag}_bench.json"), ("bench_reference.json", f"{tag}_bench_reference.json"),
-                 ("att_timeline.txt", f"{tag}_att_timeline_latest.txt")):
+                 ("bench_c4.json", f"{tag}_bench_c4.json"), ("att_timeline.txt", f"{tag}_att_timeline_latest.txt")):
     if (G / src).exists() and (G / src).stat().st_size:
         shutil.copy(G / src, P / dst)
 
@@ -60,9 +64,32 @@ with open(P / f"{tag}_launch_shares.csv", "w") as f:
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f'"{k}",{v[0]},{v[1]:.1f},{v[1] / tot:.3f}\n')
 
+# ---- localizer launch list: the LAST forward pass (profile_yolo.py runs 2 warm-up + 5 timed passes), aggregated per kernel
+if (G / "yolo_launches.csv").exists():
+    yrows = []
+    with open(G / "yolo_launches.csv") as f:
+        ylines = [ln for ln in f if ln.startswith('"')]
+    for r in csv.DictReader(ylines):
+        yrows.append((short(r["Kernel Name"]), float(r["Metric Value"].replace(",", "")) / 1e3))
+    ystarts = [i for i, r in enumerate(yrows) if r[0].startswith(("yolo_stem", "yolo_im2col0"))]
+    if ystarts:
+        last = yrows[ystarts[-1]:]
+        yagg = OrderedDict()
+        for name, us in last:
+            c = yagg.setdefault(name, [0, 0.0])
+            c[0] += 1
+            c[1] += us
+        ytot = sum(v[1] for v in yagg.values())
+        with open(P / f"{tag}_yolo_launch_shares.csv", "w") as f:
+            f.write(f"# one YOLOv5s forward (64 letterboxed 640x640 lines, split precision; {len(last)} launches) under the ncu duration-only "
+                    f"pass (cold-cache, serialised: compare SHARES)\n# total {ytot / 1e3:.3f} ms\n")
+            f.write("kernel,launches,total_us,share\n")
+            for k, v in sorted(yagg.items(), key=lambda kv: -kv[1][1]):
+                f.write(f'"{k}",{v[0]},{v[1]:.1f},{v[1] / ytot:.3f}\n')
+
 # ---- full captures
 txt = []
-for rep in ("layer_full.ncu-rep", "misc_full.ncu-rep"):
+for rep in ("layer_full.ncu-rep", "misc_full.ncu-rep", "yolo_full.ncu-rep"):
     if (G / rep).exists():
         txt.append(f"### {rep}\n" + subprocess.run([sys.executable, str(ROOT / "tools" / "ncu_summary.py"), str(G / rep)],
                                                      capture_output=True, text=True).stdout)
