@@ -221,25 +221,30 @@ int ln_gemm_f16(const LnGemmArgs& a, cudaStream_t stream) {
       (reinterpret_cast<uintptr_t>(a.beta) & 15) || (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)) || a.ldo % 8 != 0 ||
       (reinterpret_cast<uintptr_t>(a.out) & 15) || a.ldw % 8 != 0)
     return fail(EFFOCR_ERR_INVALID, "ln_gemm: operands must be 16-byte aligned with 16-byte multiple pitches");
-  constexpr int BN = 192;
+  constexpr int BN = LNQ_BN;
   using Cfg = LnQkvCfg<BN>;
   CUtensorMap tb, tc;
-  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, kLnqD, a.ldw, BN));
-  EFFOCR_TRY(make_tmap_2d(&tc, a.out, 2, a.M, a.N, a.ldo, 32, 32, 64));
+  EFFOCR_TRY(make_tmap_f16_2d(&tb, a.W, a.N, kLnqD, a.ldw, BN / 2));  // each CTA of a pair loads half of a weight tile
+  EFFOCR_TRY(make_tmap_2d(&tc, a.out, 2, a.M, a.N, a.ldo, 32, Cfg::kStoreCols, Cfg::kStoreCols * 2));
   auto kern = ln_gemm_astat_kernel<BN>;
   static bool attr_done = false;
   if (!attr_done) {
     EFFOCR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int num_m = (a.M + kBlockM - 1) / kBlockM;
-  const int grid = num_m < sm_count() ? num_m : sm_count();
+  const int num_sb = (a.M + 2 * kBlockM - 1) / (2 * kBlockM);
+  int pairs = sm_count() / 2;
+  if (num_sb < pairs) pairs = num_sb;
   EpiTmaParams ep;
   ep.bias = a.bias;
   ep.gamma = nullptr;
   {
     KernelScope ks(a.prof_tag, stream);
-    kern<<<grid, kLnqThreads, Cfg::kSmemBytes, stream>>>(a.x, a.ldx, a.gamma, a.beta, a.eps, tb, tc, a.M, a.N, ep);
+    // EFFOCR_LNQ_FLAGS: timing experiments (2: skip the LayerNorm stream, 4: skip the output stores; results are wrong)
+    static const int flags = [] { const char* e = getenv("EFFOCR_LNQ_FLAGS"); return e ? atoi(e) : 0; }();
+    long long* dbg = nullptr;  // EFFOCR_LNQ_DBG_PTR: device buffer of 3 x 1024 int64 for tools/lnq_timeline.py
+    if (const char* e = getenv("EFFOCR_LNQ_DBG_PTR")) dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
+    kern<<<2 * pairs, kLnqThreads, Cfg::kSmemBytes, stream>>>(a.x, a.ldx, a.gamma, a.beta, a.eps, tb, tc, a.M, a.N, ep, flags, dbg);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

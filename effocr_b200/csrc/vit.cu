@@ -220,12 +220,11 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     const char* e = getenv("EFFOCR_VIT_LAST_BLOCK_FULL");  // "1" = run the last block on all 197 tokens (A/B runs)
     return !(e && e[0] == '1');
   }();
-  // norm1 + QKV in one kernel (lnqkv_sm100.cuh) is bit-identical to the two-kernel path but measured SLOWER (267 us vs
-  // 71 + 176 us stand-alone at batch 1024: eight LayerNorm warps per SM cannot keep enough of x in flight); it stays an
-  // opt-in experiment: EFFOCR_LN_QKV=1
+  // norm1 + QKV in one kernel (lnqkv_sm100.cuh, CTA-pair A-stationary schedule): bit-identical to the two-kernel path and
+  // 198 us instead of 81 + 161 us per layer inside the batch-1024 step.  EFFOCR_LN_QKV=0 selects the two-kernel path.
   static const bool lnq_env = [] {
     const char* e = getenv("EFFOCR_LN_QKV");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');
   }();
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
