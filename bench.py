@@ -233,6 +233,7 @@ def kernel_work(tag: str, B: int, D: int, mlp: int, n_index: int):
         "gemm_fc1_gelu": 2.0 * M * mlp * D,
         "gemm_fc2": 2.0 * M * mlp * D,
         "mlp_fused": 4.0 * M * mlp * D,  # fc1 + GELU + fc2 + residual in one kernel
+        "block_tail": 2.0 * M * D * D + 4.0 * M * mlp * D,  # projection + residual + norm2 + fc1 + GELU + fc2 + residual
         "attention": 4.0 * B * (D // 64) * T * T * 64,
         "knn_gemm_topk": 2.0 * B * n_index * D * 3,  # three fp16 partial products per fp32 product
     }

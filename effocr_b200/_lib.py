@@ -48,6 +48,8 @@ SIGNATURES = {
                                      c_int, c_void_p]),
     "effocr_proj_ln_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_float, c_void_p,
                                    c_ll, c_int, c_int, c_void_p]),
+    "effocr_block_tail_f16": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p]),
     "effocr_crop_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_pad": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "effocr_letterbox_resize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -188,7 +188,7 @@ static void prof_drain() {
 static const char* kProfNames[PROF_NUM_TAGS] = {
     "crop_resize", "im2patch", "gemm_patch_embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1_gelu",
     "gemm_fc2", "final_layernorm", "l2_normalize", "knn_split", "knn_gemm_topk", "knn_merge_rerank", "misc",
-    "gemm_other", "conv_im2col", "yolo_misc", "nms", "dwconv_ln", "mlp_fused", "proj_ln"};
+    "gemm_other", "conv_im2col", "yolo_misc", "nms", "dwconv_ln", "mlp_fused", "proj_ln", "block_tail"};
 
 }  // namespace effocr
 

@@ -34,7 +34,7 @@ int cuda_fail(cudaError_t e, const char* what);
 enum ProfTag : int {
   PROF_CROP = 0, PROF_IM2PATCH, PROF_GEMM_PATCH, PROF_LAYERNORM, PROF_GEMM_QKV, PROF_ATTENTION, PROF_GEMM_PROJ,
   PROF_GEMM_FC1, PROF_GEMM_FC2, PROF_FINAL_LN, PROF_L2NORM, PROF_KNN_SPLIT, PROF_KNN_GEMM, PROF_KNN_MERGE, PROF_MISC,
-  PROF_GEMM_OTHER, PROF_CONV_IM2COL, PROF_YOLO_MISC, PROF_NMS, PROF_DWCONV, PROF_MLP_FUSED, PROF_PROJ_LN, PROF_NUM_TAGS
+  PROF_GEMM_OTHER, PROF_CONV_IM2COL, PROF_YOLO_MISC, PROF_NMS, PROF_DWCONV, PROF_MLP_FUSED, PROF_PROJ_LN, PROF_BLOCK_TAIL, PROF_NUM_TAGS
 };
 // Construct right before a kernel launch, destroy right after: counts the launch and, when
 // profiling is enabled, brackets it with events on `stream`.

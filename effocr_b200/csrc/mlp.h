@@ -39,4 +39,24 @@ bool proj_ln_supported(int D);
 // x += att . w^T + bias;  h = LayerNorm(x) * gamma + beta   (one kernel, full-row tiles)
 int proj_ln_f16(const ProjLnArgs& a, cudaStream_t stream);
 
+struct BlockTailArgs {
+  const __half* att = nullptr;  // [M, D] attention output, leading dimension lda
+  long long lda = 0;
+  const __half* wp = nullptr;   // [D, D] projection weight
+  const float* bp = nullptr;    // [D]
+  const float *gamma = nullptr, *beta = nullptr;  // norm2 affine [D]
+  float eps = 1e-6f;
+  const __half* w1 = nullptr;   // [HID, D]
+  const float* b1 = nullptr;
+  const __half* w2 = nullptr;   // [D, HID]
+  const float* b2 = nullptr;
+  float* x = nullptr;           // [M, D] fp32 residual stream, updated in place
+  long long ldx = 0;
+  int M = 0, D = 0, HID = 0;
+};
+
+bool block_tail_supported(int D, int HID);
+// x += att . wp^T + bp;  x += GELU(LayerNorm(x) . w1^T + b1) . w2^T + b2   (one kernel: blocktail_sm100.cuh)
+int block_tail_f16(const BlockTailArgs& a, cudaStream_t stream);
+
 }  // namespace effocr

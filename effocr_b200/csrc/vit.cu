@@ -216,6 +216,11 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     return !(e && e[0] == '0');
   }();
   const bool fused_pln = pln_env && proj_ln_supported(D);
+  static const bool tail_env = [] {
+    const char* e = getenv("EFFOCR_BLOCK_TAIL");  // "0" = proj_ln + mlp_fused as two kernels (A/B runs)
+    return !(e && e[0] == '0');
+  }();
+  const bool fused_tail = tail_env && fused_mlp && fused_pln && block_tail_supported(D, v->mlp);
   static const bool cls_env = [] {
     const char* e = getenv("EFFOCR_VIT_LAST_BLOCK_FULL");  // "1" = run the last block on all 197 tokens (A/B runs)
     return !(e && e[0] == '1');
@@ -266,6 +271,13 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
       EFFOCR_CUDA(cudaGetLastError());
     } else {
       EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
+    }
+    if (fused_tail && !last_cls) {  // projection + residual + norm2 + MLP + residual in one kernel (blocktail_sm100.cuh)
+      BlockTailArgs t;
+      t.att = v->att; t.lda = D; t.wp = L.w_proj; t.bp = L.b_proj; t.gamma = L.ln2_w; t.beta = L.ln2_b; t.eps = v->eps;
+      t.w1 = L.w_fc1; t.b1 = L.b_fc1; t.w2 = L.w_fc2; t.b2 = L.b_fc2; t.x = v->x; t.ldx = ldx; t.M = Mr; t.D = D; t.HID = v->mlp;
+      EFFOCR_TRY(block_tail_f16(t, s));
+      continue;
     }
     if (fused_pln) {  // projection + residual + norm2 in one full-row kernel: x is read and written once, no L2 reductions
       ProjLnArgs p;

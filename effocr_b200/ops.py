@@ -102,6 +102,24 @@ def proj_ln(x: torch.Tensor, att: torch.Tensor, w: torch.Tensor, bias: torch.Ten
     return out
 
 
+def block_tail(x: torch.Tensor, att: torch.Tensor, wp: torch.Tensor, bp: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+               w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """x += att @ wp.T + bp;  x += GELU(LayerNorm(x) @ w1.T + b1) @ w2.T + b2 -- in place, one fused tcgen05 kernel."""
+    lib = _lib.load()
+    x = _cuda(x, torch.float32, "x")
+    att = _cuda(att, torch.float16, "att")
+    wp, w1, w2 = _cuda(wp, torch.float16, "wp"), _cuda(w1, torch.float16, "w1"), _cuda(w2, torch.float16, "w2")
+    M, D = x.shape
+    HID = w1.shape[0]
+    assert att.shape == (M, D) and wp.shape == (D, D) and w1.shape == (HID, D) and w2.shape == (D, HID)
+    assert wp.is_contiguous() and w1.is_contiguous() and w2.is_contiguous() and x.stride(1) == 1 and att.stride(1) == 1
+    f32 = lambda t, n: _cuda(t, torch.float32, n).data_ptr()  # noqa: E731
+    _lib.check(lib.effocr_block_tail_f16(att.data_ptr(), att.stride(0), wp.data_ptr(), f32(bp, "bp"), f32(gamma, "gamma"),
+                                         f32(beta, "beta"), float(eps), w1.data_ptr(), f32(b1, "b1"), w2.data_ptr(), f32(b2, "b2"),
+                                         x.data_ptr(), x.stride(0), M, D, HID, _lib.stream_ptr()), "effocr_block_tail_f16")
+    return x
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-6,
               out_dtype=torch.float16) -> torch.Tensor:
     lib = _lib.load()

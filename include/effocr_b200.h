@@ -86,6 +86,15 @@ EFFOCR_API int effocr_proj_ln_f16(const void* d_att, long long lda, const void* 
                        long long ldx, const float* d_gamma, const float* d_beta, float eps, void* d_h, long long ldh,
                        int M, int D, void* stream);
 
+/* ---- the second half of an encoder block in one kernel (tcgen05, CTA pairs, full-row tiles) -----
+ * x[M,D] += att[M,D] . Wp[D,D]^T + bp;   x[M,D] += GELU(LayerNorm(x) * gamma + beta . W1[HID,D]^T + b1) . W2[D,HID]^T + b2.
+ * `x = x + attn(...)` (projection part) and `x = x + mlp(norm2(x))` of timm Block.forward (un-vendored;
+ * models/encoders.py:58,62-64): the residual stream is read once and written once, the normalised operand and the
+ * hidden activations stay on chip.  D = 384, HID % 128 == 0. */
+EFFOCR_API int effocr_block_tail_f16(const void* d_att, long long lda, const void* d_wp, const float* d_bp, const float* d_gamma,
+                          const float* d_beta, float eps, const void* d_w1, const float* d_b1, const void* d_w2,
+                          const float* d_b2, float* d_x, long long ldx, int M, int D, int HID, void* stream);
+
 /* ---- K1: fused crop -> square white pad -> AA bilinear 224x224 -> normalise -------------------
  * Replaces the numpy slice + `create_paired_transform` per-crop CPU path
  * (infer_effocr.py:284-293, infer_effocr_onnx_multi.py:307-340, utils/datasets_utils.py:69-90,166-172).

@@ -106,6 +106,33 @@ def test_ln_gemm_equals_layernorm_then_gemm(M, N):
     assert _rel(out, ref32) < 6e-4
 
 
+@pytest.mark.parametrize("M", [100, 256, 1576, 40000, 201728 // 4 + 77])
+def test_block_tail_equals_proj_ln_then_mlp(M):
+    """Projection + residual + norm2 + MLP + residual in one kernel against the two kernels it replaces (proj_ln, mlp_fused)
+    and against plain fp32 torch: same operands, the only arithmetic difference is that fc2 accumulates on top of the
+    residual inside the fp32 accumulator.  Row tails, one .. several tiles per CTA pair (every barrier's phase wrap)."""
+    from effocr_b200 import ops
+    torch.manual_seed(5)
+    D, HID = 384, 1536
+    x0 = torch.randn(M, D, device="cuda") * 2 + 0.5
+    att = (torch.randn(M, D, device="cuda") * 0.7).half()
+    wp = (torch.randn(D, D, device="cuda") * 0.05).half()
+    w1 = (torch.randn(HID, D, device="cuda") * 0.05).half()
+    w2 = (torch.randn(D, HID, device="cuda") * 0.05).half()
+    bp, g, be, b2 = (torch.randn(D, device="cuda") for _ in range(4))
+    b1 = torch.randn(HID, device="cuda")
+    x = x0.clone()
+    ops.block_tail(x, att, wp, bp, g, be, w1, b1, w2, b2)
+    ref = x0.clone()
+    h = ops.proj_ln(ref, att, wp, bp, g, be)
+    ops.mlp_fused(ref, h, w1, b1, w2, b2)
+    assert _rel(x, ref) < 5e-6, _rel(x, ref)  # the truncating fp32 accumulator now also carries the residual
+    t = x0 + att.float() @ wp.float().t() + bp
+    hh = torch.nn.functional.layer_norm(t, (D,), g, be, 1e-6).half().float()
+    t = t + torch.nn.functional.gelu(hh @ w1.float().t() + b1).half().float() @ w2.float().t() + b2
+    assert _rel(x, t) < 2e-4, _rel(x, t)
+
+
 @pytest.mark.parametrize("dim", [96, 192, 384, 768])
 @pytest.mark.parametrize("f32", [False, True])
 def test_layernorm(dim, f32):
