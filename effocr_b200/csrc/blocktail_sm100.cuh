@@ -30,6 +30,12 @@
 
 namespace effocr {
 
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 struct BlockTailCfg {
   static constexpr int D = 384;
   static constexpr int kKB = D / 64;
@@ -53,8 +59,16 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                        const __grid_constant__ CUtensorMap tma_w1, const __grid_constant__ CUtensorMap tma_w2,
                        const __grid_constant__ CUtensorMap tma_xl, const __grid_constant__ CUtensorMap tma_xs, int M, int HID,
                        const float* __restrict__ bp, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                       const float* __restrict__ b1, const float* __restrict__ b2, int l2_prefetch) {
+                       const float* __restrict__ b1, const float* __restrict__ b2, int l2_prefetch,
+                       int stagger, long long* __restrict__ dbg) {
   using Cfg = BlockTailCfg;
+  // timeline probe (tools/tail_timeline.py): CTA 0 stamps clock64 into dbg[role * 512 + 8 * tile + slot]
+  // (compiled in only with -DEFFOCR_TAIL_TIMELINE: the stamps cost 8 % of the kernel's time through register pressure)
+#ifdef EFFOCR_TAIL_TIMELINE
+#define BT_STAMP(role, slot) do { if (dbg && blockIdx.x == 0 && local < 60) dbg[(role) * 512 + 8 * local + (slot)] = clock64(); } while (0)
+#else
+#define BT_STAMP(role, slot) do { } while (0)
+#endif
   constexpr int D = Cfg::D, KB = Cfg::kKB, STAGES = Cfg::kStages, XS = Cfg::kXSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -67,8 +81,8 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   uint64_t* afull = wempty + STAGES;   // [KB] att k-blocks landed
   uint64_t* aempty = afull + KB;       // fc1 MMAs of the tile retired: the A region takes the next att tile
   uint64_t* tfull1 = aempty + 1;       // projection accumulators complete (and the att tile dead)
-  uint64_t* hfull = tfull1 + 1;        // h written by the epilogue warps of both CTAs
-  uint64_t* sfull = hfull + 1;
+  uint64_t* hfull = tfull1 + 1;        // [3] k-blocks 2k, 2k + 1 of h written by the epilogue warps of both CTAs
+  uint64_t* sfull = hfull + 3;
   uint64_t* sempty = sfull + 1;
   uint64_t* pfull = sempty + 1;        // [2]
   uint64_t* pempty = pfull + 2;        // [2]
@@ -78,7 +92,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                                        // slot's second use before its first has landed and read the parity of the use before)
   uint64_t* xempty = xfull + 12;       // [XS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + XS);
-  static_assert((2 * STAGES + KB + 11 + 12 + XS) * 8 + 4 <= Cfg::kBarrierBytes, "barrier area too small");
+  static_assert((2 * STAGES + KB + 13 + 12 + XS) * 8 + 4 <= Cfg::kBarrierBytes, "barrier area too small");
 
   const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -101,7 +115,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     for (int i = 0; i < KB; ++i) mbar_init(&afull[i], 1);
     mbar_init(aempty, 1);
     mbar_init(tfull1, 1);
-    mbar_init(hfull, 2 * kMlpEpiWarps);
+    for (int i = 0; i < 3; ++i) mbar_init(&hfull[i], 2 * kMlpEpiWarps);
     mbar_init(sfull, 1);
     mbar_init(sempty, 2 * kMlpEpiWarps);
     for (int i = 0; i < 2; ++i) {
@@ -122,7 +136,15 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (stagger > 0) {
+    // Every pair walks the same phases in the same time, so without this all 148 SMs read x (pass 1) and write it (drain)
+    // at the same moments and leave HBM idle during the long mlp phase: start pair p `stagger` cycles after pair p - 1.
+    const long long t_go = clock64() + static_cast<long long>(pair) * stagger;
+    while (clock64() < t_go) __nanosleep(200);
+  }
 
+  // (setmaxnreg re-distribution -- 64 / 104 or 40 / 104 registers for the control / epilogue warps -- was measured 18 % and
+  //  95 % SLOWER: ptxas then spills in the MMA issuer and the epilogue alike; every warp keeps the launch value of 96)
   if (warp_idx == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one_sync()) {
@@ -136,6 +158,8 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           if (rank == 0) mbar_arrive_expect_tx(&afull[kb], 2 * Cfg::kABytes);
           tma_load_2d_2sm(&tma_a, &afull[kb], smem_a + kb * Cfg::kABytes, kb * 64, m0);
         }
+        if (l2_prefetch & 2)  // THIS tile's residual rows towards L2 while the projection runs (pass 1 needs them next)
+          for (int c = 0; c < 12; ++c) tma_prefetch_l2_2d(&tma_xl, c * 32, m0);
         for (int kb = 0; kb < KB; ++kb) {  // Wp k-block kb: rows s*192 + rank*96 .. +96 of both N = 192 halves
           mbar_wait(&wempty[stage], phase ^ 1);
           if (rank == 0) mbar_arrive_expect_tx(&wfull[stage], 2 * Cfg::kStageBytes);
@@ -177,7 +201,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         const int m0 = tile * 256 + static_cast<int>(rank) * 128;
         mbar_wait(tfull1, local & 1);  // the projection MMAs have read the att tile: its region becomes the ring
-        if (l2_prefetch && tile + num_pairs < num_tiles) {
+        if ((l2_prefetch & 1) && tile + num_pairs < num_tiles) {
           // the NEXT tile's residual rows: HBM -> L2 now, while this tile's long tensor-bound mlp phase leaves HBM idle;
           // its ring loads (on the epilogue's critical path, the tensor pipe waits for them) then pay an L2 hit
           const int pm0 = (tile + num_pairs) * 256 + static_cast<int>(rank) * 128;
@@ -204,8 +228,10 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       uint32_t local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         // ---- projection: acc = att . Wp^T into the O columns (drained by both CTAs for the previous tile)
+        if (leader_lane) BT_STAMP(0, 0);
         mbar_wait(oempty, (local & 1) ^ 1);
         tcgen05_fence_after();
+        if (leader_lane) BT_STAMP(0, 1);   // O columns drained
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&afull[kb], local & 1);
           mbar_wait(&wfull[stage], phase);
@@ -226,8 +252,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         // ---- mlp: h is in the A region once the epilogue warps of both CTAs have written it; x' sits in the O columns
-        mbar_wait(hfull, local & 1);
-        tcgen05_fence_after();
+        if (leader_lane) BT_STAMP(0, 2);   // projection issued
         for (int j = 0; j <= NCH; ++j) {
           if (j < NCH) {  // S = h . W1_j^T  (128 hidden columns)
             const uint32_t u = local * static_cast<uint32_t>(NCH) + j;
@@ -239,15 +264,22 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
               mbar_wait(&wfull[stage], phase);
               tcgen05_fence_after();
               const uint64_t db0 = make_sw128_kmajor_desc(w_base + stage * Cfg::kStageBytes);
-              if (leader_lane) {
 #pragma unroll
-                for (int i = 0; i < KB / 2; ++i) {
-                  const int kb = kh * (KB / 2) + i;
+              for (int i = 0; i < KB / 2; ++i) {
+                const int kb = kh * (KB / 2) + i;
+                if (j == 0 && (kb & 1) == 0) {  // first chunk of the tile: h arrives two k-blocks at a time
+                  mbar_wait(&hfull[kb >> 1], local & 1);
+                  tcgen05_fence_after();
+                  if (leader_lane && kb == 4) BT_STAMP(0, 3);   // h complete
+                }
+                if (leader_lane) {
 #pragma unroll
                   for (int k = 0; k < 4; ++k)
                     umma_f16_2sm(tmem_s, da0 + (kb * Cfg::kABytes >> 4) + 2 * k, db0 + (i * Cfg::kW1KbBytes >> 4) + 2 * k, idesc1,
                                  (kb | k) ? 1u : 0u);
                 }
+              }
+              if (leader_lane) {
                 umma_commit_2sm(&wempty[stage]);
                 if (kh == 1) {
                   umma_commit_2sm(sfull);
@@ -279,7 +311,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 }
                 umma_commit_2sm(&pempty[hh]);
                 umma_commit_2sm(&wempty[stage]);
-                if (c == NCH - 1 && hh == 1) umma_commit_2sm(ofull);
+                if (c == NCH - 1 && hh == 1) { umma_commit_2sm(ofull); BT_STAMP(0, 4); }  // last fc2 MMAs issued
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -296,10 +328,14 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t local = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 0);
       mbar_wait(tfull1, local & 1);
       tcgen05_fence_after();
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 1);   // projection complete
       // ---- pass 1: x' = acc + bp + x, back into TMEM; shifted sums of this thread's 96 columns
-      float sh = 0.f, s1 = 0.f, s2 = 0.f;
+      // (packed fp32x2 arithmetic: the two passes are issue-bound, sixteen warps share four schedulers)
+      float sh = 0.f;
+      uint64_t s1p = pack2(0.f, 0.f), s2p = pack2(0.f, 0.f), nsh2 = pack2(0.f, 0.f);
 #pragma unroll 1
       for (int k = 0; k < 3; ++k) {
         const int c = k * 4 + cg, col0 = c * 32;
@@ -313,17 +349,18 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int j = 0; j < 8; ++j) {
           const float4 xo = *reinterpret_cast<const float4*>(xrow + ((j ^ (row & 7)) << 4));  // SWIZZLE_128B
           const float4 bb = __ldg(reinterpret_cast<const float4*>(bp + col0 + 4 * j));
-          float4 o;
-          o.x = xo.x + (__uint_as_float(v[4 * j]) + bb.x);
-          o.y = xo.y + (__uint_as_float(v[4 * j + 1]) + bb.y);
-          o.z = xo.z + (__uint_as_float(v[4 * j + 2]) + bb.z);
-          o.w = xo.w + (__uint_as_float(v[4 * j + 3]) + bb.w);
-          if (k == 0 && j == 0) sh = o.x;
-          const float d0 = o.x - sh, d1 = o.y - sh, d2 = o.z - sh, d3 = o.w - sh;
-          s1 += (d0 + d1) + (d2 + d3);
-          s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
-          v[4 * j] = __float_as_uint(o.x); v[4 * j + 1] = __float_as_uint(o.y);
-          v[4 * j + 2] = __float_as_uint(o.z); v[4 * j + 3] = __float_as_uint(o.w);
+          const uint64_t o01 = add2(pack2(xo.x, xo.y), add2(pack2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), pack2(bb.x, bb.y)));
+          const uint64_t o23 = add2(pack2(xo.z, xo.w), add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), pack2(bb.z, bb.w)));
+          float o0, o1, o2, o3;
+          unpack2(o01, o0, o1);
+          unpack2(o23, o2, o3);
+          if (k == 0 && j == 0) { sh = o0; nsh2 = pack2(-sh, -sh); }
+          const uint64_t d01 = add2(o01, nsh2), d23 = add2(o23, nsh2);
+          s1p = add2(s1p, add2(d01, d23));
+          s2p = fma2(d01, d01, s2p);
+          s2p = fma2(d23, d23, s2p);
+          v[4 * j] = __float_as_uint(o0); v[4 * j + 1] = __float_as_uint(o1);
+          v[4 * j + 2] = __float_as_uint(o2); v[4 * j + 3] = __float_as_uint(o3);
         }
         tmem_st_32x32b_x32(tmem_lane + col0, v);  // x': pass 2 reads it, the fc2 MMAs accumulate onto it
         named_bar_sync(1 + cg, 128);  // the four lane quarters of this column group have read the slot
@@ -331,6 +368,10 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       }
       // ---- row statistics: this thread's 96 columns -> (mean, M2), merged over the four column groups (Chan)
       {
+        float s1a, s1b, s2a, s2b;
+        unpack2(s1p, s1a, s1b);
+        unpack2(s2p, s2a, s2b);
+        const float s1 = s1a + s1b, s2 = s2a + s2b;
         const float mean_w = sh + s1 * (1.0f / 96.0f);
         const float m2_w = s2 - s1 * s1 * (1.0f / 96.0f);
         stats[(row * 4 + cg) * 2] = mean_w;
@@ -339,6 +380,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       tmem_st_wait();
       // every warp is through pass 1: the statistics are complete and no ring slot is in use, so the A region can take h
       named_bar_sync(5, kMlpEpiWarps * 32);
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 2);   // pass 1 done in every warp
       float mean, rstd;
       {
         float mw[4], m2 = 0.f;
@@ -354,7 +396,9 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int i = 0; i < 4; ++i) m2 = fmaf(96.0f * (mw[i] - mean), mw[i] - mean, m2);
         rstd = rsqrtf(m2 * (1.0f / D) + eps);
       }
-      // ---- pass 2: normalise, fp16, into the A region (K-major SWIZZLE_128B: piece p of row r at piece p ^ (r & 7))
+      // ---- pass 2: normalise, fp16, into the A region (K-major SWIZZLE_128B: piece p of row r at piece p ^ (r & 7));
+      //      chunk k of every warp completes k-blocks 2k and 2k + 1, handed to the MMA issuer pair by pair
+      const uint64_t nmean2 = pack2(-mean, -mean), rstd2 = pack2(rstd, rstd);
 #pragma unroll 1
       for (int k = 0; k < 3; ++k) {
         const int col0 = (k * 4 + cg) * 32;
@@ -372,23 +416,29 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const int c = 8 * j + 4 * t;
             const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + col0 + c));
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + col0 + c));
-            ph[2 * t] = __floats2half2_rn(fmaf((__uint_as_float(v[c]) - mean) * rstd, g4.x, b4.x),
-                                          fmaf((__uint_as_float(v[c + 1]) - mean) * rstd, g4.y, b4.y));
-            ph[2 * t + 1] = __floats2half2_rn(fmaf((__uint_as_float(v[c + 2]) - mean) * rstd, g4.z, b4.z),
-                                              fmaf((__uint_as_float(v[c + 3]) - mean) * rstd, g4.w, b4.w));
+            // ((v - mean) * rstd) * gamma + beta, the scalar kernels' operation order, two elements per instruction
+            const uint64_t n01 = mul2(add2(pack2(__uint_as_float(v[c]), __uint_as_float(v[c + 1])), nmean2), rstd2);
+            const uint64_t n23 = mul2(add2(pack2(__uint_as_float(v[c + 2]), __uint_as_float(v[c + 3])), nmean2), rstd2);
+            float h0, h1, h2, h3;
+            unpack2(fma2(n01, pack2(g4.x, g4.y), pack2(b4.x, b4.y)), h0, h1);
+            unpack2(fma2(n23, pack2(g4.z, g4.w), pack2(b4.z, b4.w)), h2, h3);
+            ph[2 * t] = __floats2half2_rn(h0, h1);
+            ph[2 * t + 1] = __floats2half2_rn(h2, h3);
           }
           *reinterpret_cast<uint4*>(hrow + (((p0 + j) ^ (row & 7)) << 4)) = pk;
         }
+        fence_proxy_async_smem();
+        if (k == 2) tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&hfull[k]);
       }
-      fence_proxy_async_smem();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(hfull);
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 3);   // pass 2 done (this warp)
       // ---- mlp: GELU of every S chunk into the P halves
       for (int j = 0; j < NCH; ++j) {
         const uint32_t u = local * static_cast<uint32_t>(NCH) + j;
         mbar_wait(sfull, u & 1);
         tcgen05_fence_after();
+        if (j == 0 && warp_idx == 4 && lane == 0) BT_STAMP(1, 4);   // first S chunk complete
         uint32_t v[2][16];
         tmem_ld_32x32b_x16(tmem_lane + Cfg::kSCol + cg * 16, v[0]);
         tmem_ld_32x32b_x16(tmem_lane + Cfg::kSCol + 64 + cg * 16, v[1]);
@@ -420,12 +470,14 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         }
       }
       // ---- drain: O (= x' + fc2) + b2 -> plain TMA stores into x (eight warps, 32 x 32 fp32 boxes through the idle P buffers)
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 5);   // last GELU chunk written
       constexpr int OCH = D / 2 / 32;
       const int m_row0 = tile * 256 + static_cast<int>(rank) * 128 + q * 32;
       if (cg < 2) {
         uint8_t* stg = smem_p + ((warp_idx - 4) & 7) * 4096;
         mbar_wait(ofull, local & 1);
         tcgen05_fence_after();
+        if (warp_idx == 4 && lane == 0) BT_STAMP(1, 6);   // fc2 complete
         uint32_t v[32];
 #pragma unroll
         for (int c = 0; c < OCH; ++c) {
@@ -461,12 +513,14 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         __syncwarp();
       }
       named_bar_sync(5, kMlpEpiWarps * 32);  // staging reads done before the P region holds the next tile's statistics
+      if (warp_idx == 4 && lane == 0) BT_STAMP(1, 7);   // tile drained
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
   tcgen05_fence_before();
   cluster_sync_all();
   if (warp_idx == 2) tmem_dealloc_2sm(tmem_base, 512);
+#undef BT_STAMP
 }
 
 }  // namespace effocr

@@ -126,7 +126,9 @@ def test_block_tail_equals_proj_ln_then_mlp(M):
     ref = x0.clone()
     h = ops.proj_ln(ref, att, wp, bp, g, be)
     ops.mlp_fused(ref, h, w1, b1, w2, b2)
-    assert _rel(x, ref) < 5e-6, _rel(x, ref)  # the truncating fp32 accumulator now also carries the residual
+    # not bit-equal: the fp32 accumulator also carries the residual, and the row statistics are summed two lanes at a time
+    # (packed fp32x2), which flips the fp16 rounding of an occasional h element
+    assert _rel(x, ref) < 5e-5, _rel(x, ref)
     t = x0 + att.float() @ wp.float().t() + bp
     hh = torch.nn.functional.layer_norm(t, (D,), g, be, 1e-6).half().float()
     t = t + torch.nn.functional.gelu(hh @ w1.float().t() + b1).half().float() @ w2.float().t() + b2
