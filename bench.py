@@ -757,6 +757,8 @@ def main():
         def eff_launches(tag, cnt):
             """Launches per step weighted by their size: the last block's launch covers 1 of 197 rows per crop."""
             n = cnt / prof_steps
+            if tag in ("mlp_fused", "proj_ln") and "block_tail" in prof:
+                return n / 197  # with the block-tail kernel these two only run the last block's class-token rows
             if tag in LAST_BLOCK_TAGS and n > 1:
                 return n - 1 + 1.0 / 197
             if tag == "layernorm" and "proj_ln" not in prof and n > 1:

@@ -113,10 +113,14 @@ def traffic_of(rep):
 
 traffic = {}
 if (G / "layer_full.ncu-rep").exists():
-    # tools/profile_gemm.py launch order: qkv, attention, fused proj + residual + LN, layernorm, fused MLP block
-    order = ["gemm_qkv", "attention", "proj_ln", "layernorm", "mlp_fused"]
-    for name, (_, t) in zip(order, traffic_of("layer_full.ncu-rep")):
-        traffic[name] = t
+    # tools/profile_gemm.py: the product kernels (norm1 + QKV, attention, block tail) and the ones they replaced, by name
+    names = [("ln_gemm_astat", "gemm_qkv"), ("block_tail", "block_tail"), ("attention", "attention"), ("proj_ln", "proj_ln"),
+             ("layernorm_rows", "layernorm"), ("mlp_fused", "mlp_fused"), ("gemm_tn", "gemm_qkv_two_kernel_path")]
+    for kname, t in traffic_of("layer_full.ncu-rep"):
+        for sub, key in names:
+            if sub in kname:
+                traffic.setdefault(key, t)
+                break
 if (G / "misc_full.ncu-rep").exists():
     for kname, t in traffic_of("misc_full.ncu-rep"):
         for key in ("crop_resize", "knn_gemm_topk", "knn_merge_rerank"):

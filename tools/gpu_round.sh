@@ -21,7 +21,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python tools/profile_yolo.py 64 > $O/yolo_prof.log 2>&1; echo "rc=$?"
 echo "== ncu full (one ViT-S layer)"
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"gemm_tn|attention|layernorm_rows|mlp_fused|proj_ln" -s 5 -c 5 -f -o $O/layer_full \
+    -k regex:"gemm_tn|attention|layernorm_rows|mlp_fused|proj_ln|ln_gemm_astat|block_tail" -s 8 -c 8 -f -o $O/layer_full \
     python tools/profile_gemm.py 2 > $O/ncu_full.log 2>&1; echo "rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on \
     -k regex:"crop_resize|knn_" -c 8 -f -o $O/misc_full \

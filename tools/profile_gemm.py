@@ -1,5 +1,6 @@
-"""ncu target: one ViT-S layer at batch 1024 (M = 201728): QKV GEMM, attention, fused proj + residual + LayerNorm, LayerNorm, fused MLP block;
-one launch each after warm-up."""
+"""ncu target: one ViT-S layer at batch 1024 (M = 201728).  The product path is three kernels -- norm1 + QKV (ln_gemm), attention,
+block tail (projection + residual + norm2 + MLP + residual) -- followed here by the kernels they replaced (QKV GEMM, proj_ln, LayerNorm,
+mlp_fused) for comparison; one launch each per repetition after warm-up."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -22,6 +23,9 @@ g = torch.ones(384, device=dev)
 h2 = torch.empty(M, 384, device=dev, dtype=torch.float16)
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 for _ in range(reps):
+    ops.ln_gemm(x, g, b384, wqkv, bias=b1152, out=qkv)      # norm1 + QKV projection in one kernel
+    ops.attention(qkv, 1024, 6)
+    ops.block_tail(x, h, wproj, b384, g, b384, wfc1, b1536, wfc2, b384)  # projection + residual + norm2 + MLP + residual
     ops.gemm(h, wqkv, bias=b1152, out=qkv)
     ops.attention(qkv, 1024, 6)
     ops.proj_ln(x, h, wproj, b384, g, b384, out=h2)  # projection + residual + norm2 in one kernel
