@@ -176,19 +176,35 @@ class EffOCRPipeline:
         return {"packed": packed_images, "per_line": per_line, "boxes": boxes, "n": n, "event": done}
 
     def launch_recognize(self, st):
-        """Stage 2a on the CURRENT stream, asynchronous: crop -> encoder -> kNN for every character of the batch.
-        Returns the device id tensor (or None); nothing is synchronised."""
+        """Stage 2a on the CURRENT stream, asynchronous: crop -> encoder -> kNN for every character of the batch, then the
+        ids into a pinned host buffer with an asynchronous copy.  Returns (host ids, event) or None; nothing is
+        synchronised, so the next batch's kernels can be enqueued behind this one before its ids are read."""
         if not st["n"]:
             return None
         torch.cuda.current_stream().wait_event(st["event"])
         _dist, idx, _ = self.recognizer.recognize_device(st["packed"][0], st["packed"][1], st["boxes"], st["n"], self.knn)
-        return idx
+        ring = getattr(self, "_id_ring", None)
+        if ring is None:
+            ring = self._id_ring = {"bufs": [None] * 3, "next": 0}  # three batches can be between launch and finish
+        slot = ring["next"]
+        ring["next"] = (slot + 1) % len(ring["bufs"])
+        buf = ring["bufs"][slot]
+        if buf is None or buf.shape[0] < idx.shape[0] or buf.shape[1] != idx.shape[1] or buf.dtype != idx.dtype:
+            # pinned allocations synchronise the device and take a driver-wide lock: all three at once, generously sized
+            rows = max(2 * int(idx.shape[0]), 4096)
+            ring["bufs"] = [torch.empty((rows, idx.shape[1]), dtype=idx.dtype, pin_memory=True) for _ in ring["bufs"]]
+            buf = ring["bufs"][slot]
+        host = buf[:idx.shape[0]]
+        host.copy_(idx, non_blocking=True)
+        return host, torch.cuda.current_stream().record_event()
 
     def finish_recognize(self, st, idx):
-        """Stage 2b: ids to the host (synchronises the current stream), decode + en_postprocess."""
+        """Stage 2b: wait for the batch's ids (its own event, not the stream), decode + en_postprocess."""
         results = []
         if idx is not None:
-            idx = idx.cpu().numpy()
+            host, event = idx
+            event.synchronize()
+            idx = host.numpy()
         pos = 0
         for (char_b, wei, heights, bottoms, rects) in st["per_line"]:
             n = len(rects)
@@ -221,8 +237,8 @@ class EffOCRPipeline:
         """Yield the per-line results of each batch in order.  With overlap the reference's three barriered phases
         become a software pipeline on ONE host thread: the recognizer kernels of batch i are enqueued without a
         host synchronisation, then stage 1 of batch i+1 (pinned-memory packing, upload, letterbox, YOLOv5s, NMS, host
-        box logic) runs on a second CUDA stream while the GPU works through batch i, and only then are the ids of
-        batch i fetched and decoded.  (A worker thread was tried first: the two Python threads fought over the GIL
+        box logic) runs on a second CUDA stream while the GPU works through batch i, recognize(i+1) is enqueued behind it,
+        and only then are the ids of batch i (copied to pinned memory asynchronously) decoded.  (A worker thread was tried first: the two Python threads fought over the GIL
         and the pipeline got slower.)  Results are identical to the sequential order: the stages share no mutable
         state and every kernel is deterministic."""
         # `batches` is consumed lazily, one batch ahead of the one being recognised, so that a decoding iterator
@@ -247,14 +263,21 @@ class EffOCRPipeline:
             with torch.cuda.stream(side):
                 return self.stage_localize(chunk)
 
+        # order per iteration: enqueue recognize(i) -> decode batch i-1 (its ids arrived long ago) -> stage 1 of batch i+1 on
+        # the side stream (the host blocks on ITS detections while the GPU runs recognize(i)) -> next iteration enqueues
+        # recognize(i+1) behind recognize(i) before anything waits for batch i: the GPU never idles on a host round trip
         st, nxt = stage1(first), second
+        prev = None
         while True:
-            idx = self.launch_recognize(st) if st is not None else None
+            handle = self.launch_recognize(st) if st is not None else None
+            if prev is not None:
+                yield self.finish_recognize(*prev) if prev[0] is not None else []
             st_next = stage1(nxt) if nxt is not None else None
-            yield self.finish_recognize(st, idx) if st is not None else []
+            prev = (st, handle)
             if nxt is None:
                 break
             st, nxt = st_next, next(it, None)
+        yield self.finish_recognize(*prev) if prev[0] is not None else []
 
 
 def run_effocr_sharded(images_rgb, pipeline, keys=None, batch_lines: int = 64, weights=None):
