@@ -69,6 +69,11 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
 #else
 #define BT_STAMP(role, slot) do { } while (0)
 #endif
+#ifdef EFFOCR_TAIL_TIMELINE
+#define BT_WAIT(acc, ...) do { const long long _t = clock64(); __VA_ARGS__; (acc) += clock64() - _t; } while (0)
+#else
+#define BT_WAIT(acc, ...) do { __VA_ARGS__; } while (0)
+#endif
   constexpr int D = Cfg::D, KB = Cfg::kKB, STAGES = Cfg::kStages, XS = Cfg::kXSlots;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -226,15 +231,16 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       int stage = 0;
       uint32_t phase = 0;
       uint32_t local = 0;
+      long long w_o = 0, w_a = 0, w_w = 0, w_h = 0, w_s = 0, w_p = 0;  // cycles waited per barrier class (timeline build)
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
         // ---- projection: acc = att . Wp^T into the O columns (drained by both CTAs for the previous tile)
         if (leader_lane) BT_STAMP(0, 0);
-        mbar_wait(oempty, (local & 1) ^ 1);
+        BT_WAIT(w_o, mbar_wait(oempty, (local & 1) ^ 1));
         tcgen05_fence_after();
         if (leader_lane) BT_STAMP(0, 1);   // O columns drained
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&afull[kb], local & 1);
-          mbar_wait(&wfull[stage], phase);
+          BT_WAIT(w_a, mbar_wait(&afull[kb], local & 1));
+          BT_WAIT(w_w, mbar_wait(&wfull[stage], phase));
           tcgen05_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(a_base + kb * Cfg::kABytes);
           const uint64_t dw0 = make_sw128_kmajor_desc(w_base + stage * Cfg::kStageBytes);
@@ -256,19 +262,19 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
         for (int j = 0; j <= NCH; ++j) {
           if (j < NCH) {  // S = h . W1_j^T  (128 hidden columns)
             const uint32_t u = local * static_cast<uint32_t>(NCH) + j;
-            mbar_wait(sempty, (u & 1) ^ 1);
+            BT_WAIT(w_s, mbar_wait(sempty, (u & 1) ^ 1));
             const uint32_t tmem_s = tmem_base + Cfg::kSCol;
             const uint64_t da0 = make_sw128_kmajor_desc(a_base);
 #pragma unroll
             for (int kh = 0; kh < 2; ++kh) {
-              mbar_wait(&wfull[stage], phase);
+              BT_WAIT(w_w, mbar_wait(&wfull[stage], phase));
               tcgen05_fence_after();
               const uint64_t db0 = make_sw128_kmajor_desc(w_base + stage * Cfg::kStageBytes);
 #pragma unroll
               for (int i = 0; i < KB / 2; ++i) {
                 const int kb = kh * (KB / 2) + i;
                 if (j == 0 && (kb & 1) == 0) {  // first chunk of the tile: h arrives two k-blocks at a time
-                  mbar_wait(&hfull[kb >> 1], local & 1);
+                  BT_WAIT(w_h, mbar_wait(&hfull[kb >> 1], local & 1));
                   tcgen05_fence_after();
                   if (leader_lane && kb == 4) BT_STAMP(0, 3);   // h complete
                 }
@@ -295,8 +301,8 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
             const uint32_t u = local * static_cast<uint32_t>(NCH) + c;
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-              mbar_wait(&pfull[hh], u & 1);
-              mbar_wait(&wfull[stage], phase);
+              BT_WAIT(w_p, mbar_wait(&pfull[hh], u & 1));
+              BT_WAIT(w_w, mbar_wait(&wfull[stage], phase));
               tcgen05_fence_after();
               const uint64_t dp0 = make_sw128_kmajor_desc(p_base + hh * Cfg::kPBytes);
               const uint32_t wst = w_base + stage * Cfg::kStageBytes;
@@ -312,6 +318,11 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                 umma_commit_2sm(&pempty[hh]);
                 umma_commit_2sm(&wempty[stage]);
                 if (c == NCH - 1 && hh == 1) { umma_commit_2sm(ofull); BT_STAMP(0, 4); }  // last fc2 MMAs issued
+#ifdef EFFOCR_TAIL_TIMELINE
+                if (dbg && blockIdx.x == 0 && c == NCH - 1 && hh == 1) {
+                  dbg[1000] = w_o; dbg[1001] = w_a; dbg[1002] = w_w; dbg[1003] = w_h; dbg[1004] = w_s; dbg[1005] = w_p; dbg[1006] = local + 1;
+                }
+#endif
               }
               __syncwarp();
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
