@@ -737,7 +737,7 @@ template <bool kDbg, int kAblate = 0, bool kTmaOut = true>
 __global__ void __launch_bounds__(kAtThreads, 1)
 attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_kv,
                       const __grid_constant__ CUtensorMap tma_o,
-                    __half* __restrict__ out, int batch, int H, float scale_log2e, long long* dbg) {
+                    __half* __restrict__ out, int batch, int H, float scale_log2e, long long* dbg, int reverse) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem;                              // [2 groups] x 16 KB
@@ -801,7 +801,8 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     if (elect_one_sync()) {
       int it = 0;  // pair counter of this CTA
       for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
-        const int b = bh / H, h = bh % H;
+        const int bhr = reverse ? num_bh - 1 - bh : bh;  // walk the units backwards: see vit.cu (L2-friendly kernel order)
+        const int b = bhr / H, h = bhr % H;
         const int row0 = b * kAtT;
         const int s = it & 1;
         const uint32_t par = it & 1, par2 = (it >> 1) & 1;
@@ -928,7 +929,8 @@ attention_tc2b_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_co
     int it = 0;
     long long a_s = 0, a_c = 0, a_o = 0, a_e = 0;  // dbg: cycles in the s_full wait / softmax / o_full wait / epilogue
     for (int bh = blockIdx.x; bh < num_bh; bh += gridDim.x, ++it) {
-      const int b = bh / H, h = bh % H;
+      const int bhr = reverse ? num_bh - 1 - bh : bh;
+      const int b = bhr / H, h = bhr % H;
       const uint32_t par = it & 1;
       const long long ts0 = kDbg ? clock64() : 0;
       mbar_wait(&s_full[g], par);

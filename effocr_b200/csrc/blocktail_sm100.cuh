@@ -60,7 +60,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
                        const __grid_constant__ CUtensorMap tma_xl, const __grid_constant__ CUtensorMap tma_xs, int M, int HID,
                        const float* __restrict__ bp, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        const float* __restrict__ b1, const float* __restrict__ b2, int l2_prefetch,
-                       int stagger, long long* __restrict__ dbg) {
+                       int stagger, int reverse, long long* __restrict__ dbg) {
   using Cfg = BlockTailCfg;
   // timeline probe (tools/tail_timeline.py): CTA 0 stamps clock64 into dbg[role * 512 + 8 * tile + slot]
   // (compiled in only with -DEFFOCR_TAIL_TIMELINE: the stamps cost 8 % of the kernel's time through register pressure)
@@ -143,11 +143,18 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   if (stagger > 0) {
     // Every pair walks the same phases in the same time, so without this all 148 SMs read x (pass 1) and write it (drain)
-    // at the same moments and leave HBM idle during the long mlp phase: start pair p `stagger` cycles after pair p - 1.
-    const long long t_go = clock64() + static_cast<long long>(pair) * stagger;
+    // at the same moments and leave HBM idle during the long mlp phase.  `stagger` = estimated cycles per tile.  Pairs
+    // that own one tile fewer than the others (pair >= rem) have a tile's worth of slack at the end: their starts are
+    // spread over most of a tile; the pairs on the critical path are spread over 15 % of one.
+    const int rem = num_tiles % num_pairs;
+    long long delay = 0;
+    if (num_tiles > num_pairs) {
+      if (rem == 0 || pair < rem) delay = static_cast<long long>(stagger) * 15 / 100 * pair / (rem == 0 ? num_pairs : rem);
+      else delay = static_cast<long long>(stagger) * (20 + 70 * (pair - rem) / (num_pairs - rem)) / 100;
+    }
+    const long long t_go = clock64() + delay;
     while (clock64() < t_go) __nanosleep(200);
   }
-
   // (setmaxnreg re-distribution -- 64 / 104 or 40 / 104 registers for the control / epilogue warps -- was measured 18 % and
   //  95 % SLOWER: ptxas then spills in the MMA issuer and the epilogue alike; every warp keeps the launch value of 96)
   if (warp_idx == 0) {
@@ -157,7 +164,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       uint32_t phase = 0;
       uint32_t local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
-        const int m0 = tile * 256 + static_cast<int>(rank) * 128;
+        const int m0 = (reverse ? num_tiles - 1 - tile : tile) * 256 + static_cast<int>(rank) * 128;
         mbar_wait(aempty, (local & 1) ^ 1);  // fc1 MMAs of the previous tile have retired: the A region is free
         for (int kb = 0; kb < KB; ++kb) {
           if (rank == 0) mbar_arrive_expect_tx(&afull[kb], 2 * Cfg::kABytes);
@@ -204,7 +211,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
     if (elect_one_sync()) {
       uint32_t local = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local) {
-        const int m0 = tile * 256 + static_cast<int>(rank) * 128;
+        const int m0 = (reverse ? num_tiles - 1 - tile : tile) * 256 + static_cast<int>(rank) * 128;
         mbar_wait(tfull1, local & 1);  // the projection MMAs have read the att tile: its region becomes the ring
         if ((l2_prefetch & 1) && tile + num_pairs < num_tiles) {
           // the NEXT tile's residual rows: HBM -> L2 now, while this tile's long tensor-bound mlp phase leaves HBM idle;
@@ -483,7 +490,7 @@ block_tail_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_c
       // ---- drain: O (= x' + fc2) + b2 -> plain TMA stores into x (eight warps, 32 x 32 fp32 boxes through the idle P buffers)
       if (warp_idx == 4 && lane == 0) BT_STAMP(1, 5);   // last GELU chunk written
       constexpr int OCH = D / 2 / 32;
-      const int m_row0 = tile * 256 + static_cast<int>(rank) * 128 + q * 32;
+      const int m_row0 = (reverse ? num_tiles - 1 - tile : tile) * 256 + static_cast<int>(rank) * 128 + q * 32;
       if (cg < 2) {
         uint8_t* stg = smem_p + ((warp_idx - 4) & 7) * 4096;
         mbar_wait(ofull, local & 1);

@@ -244,7 +244,8 @@ int ln_gemm_f16(const LnGemmArgs& a, cudaStream_t stream) {
     static const int flags = [] { const char* e = getenv("EFFOCR_LNQ_FLAGS"); return e ? atoi(e) : 0; }();
     long long* dbg = nullptr;  // EFFOCR_LNQ_DBG_PTR: device buffer of 3 x 1024 int64 for tools/lnq_timeline.py
     if (const char* e = getenv("EFFOCR_LNQ_DBG_PTR")) dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
-    kern<<<2 * pairs, kLnqThreads, Cfg::kSmemBytes, stream>>>(a.x, a.ldx, a.gamma, a.beta, a.eps, tb, tc, a.M, a.N, ep, flags, dbg);
+    kern<<<2 * pairs, kLnqThreads, Cfg::kSmemBytes, stream>>>(a.x, a.ldx, a.gamma, a.beta, a.eps, tb, tc, a.M, a.N, ep,
+                                                              flags | (a.reverse ? 256 : 0), dbg);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

@@ -41,6 +41,7 @@ struct LnGemmArgs {
   long long ldo = 0;
   int M = 0, N = 0, D = 0;
   int prof_tag = PROF_GEMM_QKV;
+  int reverse = 0;  // walk the row blocks from the last to the first (L2-friendly kernel order, vit.cu)
 };
 bool ln_gemm_supported(int D, int N);
 // out = (LayerNorm(x) * gamma + beta) . W^T + bias in one kernel: the normalised operand never reaches HBM

@@ -208,7 +208,7 @@ ln_gemm_astat_kernel(const float* __restrict__ x, long long ldx, const float* __
       for (int nb = 0; nb < num_n; ++nb, ++local) {
         const int as = local & 1;
         const uint32_t aphase = (local >> 1) & 1;
-        const int m0 = sb * 2 * kBlockM + rank * kBlockM + q * 32;
+        const int m0 = ((flags & 256) ? num_sb - 1 - sb : sb) * 2 * kBlockM + rank * kBlockM + q * 32;  // bit 8: walk the row blocks backwards
         const int n0 = nb * BLOCK_N + half * (BLOCK_N / 2);
         const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + half * (BLOCK_N / 2);
         if (warp_idx == 4 && lane == 0) LNQ_STAMP(1, 3 * local);
@@ -281,7 +281,7 @@ ln_gemm_astat_kernel(const float* __restrict__ x, long long ldx, const float* __
     const int total = nblk * R;  // rows in this warp's stream
     auto issue = [&](int n, int slot) {  // lane 0: row n of the stream into `slot`
       const int sb = pair + (n / R) * num_pairs;
-      int row = sb * 2 * kBlockM + rank * kBlockM + lw * R + (n % R);
+      int row = ((flags & 256) ? num_sb - 1 - sb : sb) * 2 * kBlockM + rank * kBlockM + lw * R + (n % R);
       row = row < M ? row : M - 1;
       mbar_arrive_expect_tx(&xfull[slot], Cfg::kXRowBytes);
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

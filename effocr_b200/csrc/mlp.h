@@ -53,6 +53,7 @@ struct BlockTailArgs {
   float* x = nullptr;           // [M, D] fp32 residual stream, updated in place
   long long ldx = 0;
   int M = 0, D = 0, HID = 0;
+  int reverse = 0;  // walk the tiles from the last to the first (L2-friendly kernel order, vit.cu)
 };
 
 bool block_tail_supported(int D, int HID);

@@ -84,12 +84,12 @@ int block_tail_f16(const BlockTailArgs& a, cudaStream_t stream) {
   if (tiles < pairs) pairs = tiles;
   {
     KernelScope ks(PROF_BLOCK_TAIL, stream);
-    static const int stagger = [] { const char* e = getenv("EFFOCR_TAIL_STAGGER"); return e ? atoi(e) : 400; }();  // cycles per pair (A/B: 460 us at 0, 452 us at 300-500)
+    static const int stagger = [] { const char* e = getenv("EFFOCR_TAIL_STAGGER"); return e ? atoi(e) : 72000; }();  // estimated cycles per tile (0 = no stagger)
     long long* dbg = nullptr;  // EFFOCR_TAIL_DBG_PTR: device buffer of 2 x 512 int64 for tools/tail_timeline.py
     if (const char* e = getenv("EFFOCR_TAIL_DBG_PTR")) dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 0));
     static const int l2_prefetch = [] { const char* e = getenv("EFFOCR_TAIL_PREFETCH"); return e ? atoi(e) : 0; }();  // A/B: 466 us without, 488 us with (stand-alone, batch 1024)
     block_tail_pair_kernel<<<2 * pairs, kMlpThreads, Cfg::kSmemBytes, stream>>>(ta, twp, tw1, tw2, txl, txs, a.M, a.HID, a.bp, a.gamma,
-                                                                                a.beta, a.eps, a.b1, a.b2, l2_prefetch, stagger, dbg);
+                                                                                a.beta, a.eps, a.b1, a.b2, l2_prefetch, stagger, a.reverse, dbg);
   }
   EFFOCR_CUDA(cudaGetLastError());
   return EFFOCR_OK;

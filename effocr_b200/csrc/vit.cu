@@ -89,7 +89,7 @@ int layernorm_f32(const float* x, long long ldx, const float* g, const float* b,
 // impl 0: tcgen05 kernel, one TMEM pass over S with two key blocks combined flash-attention style (default); A/B
 // variants via EFFOCR_ATTENTION_SOFTMAX or impl: 5 = three key blocks / 16 softmax warps, 2 = two TMEM passes, 3 (env 1) = single pass via fp16 deltas in the P
 // tile, 4 = two passes with 16 softmax warps; impl 1: first-generation mma.sync kernel
-int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0) {
+int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaStream_t s, int impl = 0, int reverse = 0) {
   if (T != 197) return fail(EFFOCR_ERR_INVALID, "attention: sequence length must be 197 (ViT/16 @ 224)");
   const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
 #ifdef EFFOCR_AB
@@ -176,14 +176,14 @@ int attention_f16(const __half* qkv, __half* out, int batch, int T, int H, cudaS
 #define EFFOCR_ATT_ABL(m)                                                                                              \
   if (abl == m) {                                                                                                      \
     EFFOCR_CUDA(cudaFuncSetAttribute(attention_tc2b_kernel<false, m, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes)); \
-    attention_tc2b_kernel<false, m, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);        \
+    attention_tc2b_kernel<false, m, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr, reverse);        \
   } else
       EFFOCR_ATT_ABL(1) EFFOCR_ATT_ABL(2) EFFOCR_ATT_ABL(4) EFFOCR_ATT_ABL(8) EFFOCR_ATT_ABL(3) EFFOCR_ATT_ABL(7) EFFOCR_ATT_ABL(15)
 #undef EFFOCR_ATT_ABL
 #endif
-      if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, dbg);
-      else if (!tma_out) attention_tc2b_kernel<false, 0, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);
-      else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr);
+      if (dbg) attention_tc2b_kernel<true><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, dbg, reverse);
+      else if (!tma_out) attention_tc2b_kernel<false, 0, false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr, reverse);
+      else attention_tc2b_kernel<false><<<grid, kAtThreads, kAtSmemBytes, s>>>(tq, tkv, to, out, batch, H, scale_log2e, nullptr, reverse);
     }
   }
   EFFOCR_CUDA(cudaGetLastError());
@@ -231,6 +231,16 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
     const char* e = getenv("EFFOCR_LN_QKV");
     return !(e && e[0] == '0');
   }();
+  // EFFOCR_SNAKE=1 (A/B, off): every persistent kernel finishes with the highest (or lowest) rows of its output still in the
+  // 126 MB L2; the next kernel then walks its tiles from THAT end, the direction flipping with every kernel of the
+  // three-kernel layer.  Measured: no difference (11.07 ms per step either way) -- two or three waves of reads are not
+  // where the kernels wait.
+  static const bool snake_env = [] {
+    const char* e = getenv("EFFOCR_SNAKE");
+    return e && e[0] == '1';
+  }();
+  int dir = 1;  // 1: the previous kernel walked forwards (the patch-embedding GEMM does), so the next one walks backwards
+  auto next_reverse = [&]() { const int r = snake_env ? dir : 0; dir ^= 1; return r; };
   for (int l = 0; l < v->depth; ++l) {
     const VitLayer& L = v->layers[l];
     const bool last_cls = cls_env && l == v->depth - 1;
@@ -239,6 +249,7 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
       LnGemmArgs q;
       q.x = v->x; q.ldx = D; q.gamma = L.ln1_w; q.beta = L.ln1_b; q.eps = v->eps; q.W = L.w_qkv; q.ldw = D; q.bias = L.b_qkv;
       q.out = v->qkv; q.ldo = 3 * D; q.M = M; q.N = 3 * D; q.D = D; q.prof_tag = PROF_GEMM_QKV;
+      q.reverse = next_reverse();
       EFFOCR_TRY(ln_gemm_f16(q, s));
     } else {
     EFFOCR_TRY(layernorm_f16(v->x, D, L.ln1_w, L.ln1_b, v->h16, D, M, D, v->eps, s, PROF_LAYERNORM));
@@ -270,12 +281,13 @@ static int vit_forward_chunk(VitHandle* v, int B, float* emb, cudaStream_t s) {
       cls_attention_kernel<<<(B * v->H + 3) / 4, 128, 0, s>>>(v->qkv, v->att, B, T, v->H, 0.125f);
       EFFOCR_CUDA(cudaGetLastError());
     } else {
-      EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s));
+      EFFOCR_TRY(attention_f16(v->qkv, v->att, B, T, v->H, s, 0, (lnq_env && fused_tail) ? next_reverse() : 0));
     }
     if (fused_tail && !last_cls) {  // projection + residual + norm2 + MLP + residual in one kernel (blocktail_sm100.cuh)
       BlockTailArgs t;
       t.att = v->att; t.lda = D; t.wp = L.w_proj; t.bp = L.b_proj; t.gamma = L.ln2_w; t.beta = L.ln2_b; t.eps = v->eps;
       t.w1 = L.w_fc1; t.b1 = L.b_fc1; t.w2 = L.w_fc2; t.b2 = L.b_fc2; t.x = v->x; t.ldx = ldx; t.M = Mr; t.D = D; t.HID = v->mlp;
+      t.reverse = lnq_env ? next_reverse() : 0;
       EFFOCR_TRY(block_tail_f16(t, s));
       continue;
     }
