@@ -28,7 +28,8 @@ constexpr int kKnnStages = 4;
 constexpr int kKnnThreads = 384;
 constexpr int kKnnStageBytes = (kKnnBM + kKnnBN) * kKnnBK * 2;            // 32 KB
 constexpr int kKnnListBytes = 256 * kKnnCap * 8;                           // 64 KB
-constexpr int kKnnSmemBytes = kKnnStages * kKnnStageBytes + kKnnListBytes + 512 + 1024;
+constexpr int kKnnScoreBytes = 256 * 32 * 4;                               // 32 KB: one 32-column chunk of scores per epilogue thread
+constexpr int kKnnSmemBytes = kKnnStages * kKnnStageBytes + kKnnListBytes + kKnnScoreBytes + 512 + 1024;
 
 // x fp32 [rows, D] -> fp16 [rows_pad, 3 * Dp]:  mode 0 (queries) [hi | hi | lo], mode 1 (index) [hi | lo | hi];
 // lo = fp16((x - hi) * 2048); padding rows / columns are zero.
@@ -95,7 +96,8 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   uint8_t* smem_b = smem + kKnnStages * kKnnBM * kKnnBK * 2;
   float* list_val = reinterpret_cast<float*>(smem + kKnnStages * kKnnStageBytes);
   int* list_idx = reinterpret_cast<int*>(list_val + 256 * kKnnCap);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kKnnStages * kKnnStageBytes + kKnnListBytes);
+  float* score_buf = reinterpret_cast<float*>(smem + kKnnStages * kKnnStageBytes + kKnnListBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kKnnStages * kKnnStageBytes + kKnnListBytes + kKnnScoreBytes);
   uint64_t* empty_bar = full_bar + kKnnStages;
   uint64_t* tfull_bar = empty_bar + kKnnStages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -192,10 +194,26 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
         tmem_ld_32x32b_x32(ta + 128, v2);
         tmem_ld_wait();
         const int n0 = nt * kKnnBN + col0;
+        // Candidates that can still enter this thread's list, judged against the list as it stands now (its minimum only
+        // rises): a bit mask, the scores parked in shared memory.  The warp then loops while ANY lane has candidates left,
+        // every lane taking its next one in ascending id order -- the same sequence of insertions per thread as testing
+        // the 32 candidates one by one, but max-over-lanes(popcount) warp-wide insert calls per chunk instead of one for
+        // every candidate that any of the 32 lanes wants (4x fewer at 10 000 prototypes).
+        uint32_t cand = 0;
+        float* sb = score_buf + e;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float sc = fmaf(__uint_as_float(v2[i]), 4.8828125e-4f, __uint_as_float(v1[i]));
-          if (n0 + i < N && (st.count < CAP || sc > st.minv)) st = knn_insert<CAP>(st, sc, n0 + i, lv, li);
+          sb[i * 256] = sc;
+          if (n0 + i < N && (st.count < CAP || sc > st.minv)) cand |= 1u << i;
+        }
+        while (__any_sync(0xffffffffu, cand != 0)) {
+          if (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float sc = sb[i * 256];
+            if (st.count < CAP || sc > st.minv) st = knn_insert<CAP>(st, sc, n0 + i, lv, li);
+          }
         }
       }
       tcgen05_fence_before();
