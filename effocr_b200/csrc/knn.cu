@@ -235,8 +235,12 @@ knn_gemm_topk_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_con
   if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// One warp per query: merge `nparts` short-lists down to the best 32 by (approx score desc, id asc),
-// re-score those with fp32 FMAs against the fp32 index, order by (exact score desc, id asc), emit k.
+// One warp per query: merge `nparts` short-lists down to the best `cap` (16 for k <= 10, else 32) by (approx score desc,
+// id asc) -- the same margin argument as for the per-partition lists: the spare places absorb re-orderings by the ~2^-22
+// relative error of the split-fp16 scores -- re-score those with fp32 FMAs against the fp32 index, order by (exact score
+// desc, id asc), emit k.  The candidates are pulled into registers once (PER per lane) when they fit: the selection rounds
+// are a dependent chain, and re-reading the lists from memory in every round made the kernel pure load latency.
+constexpr int kKnnMergePer = 24;  // candidates per lane held in registers: nparts * cap <= 768
 __global__ void __launch_bounds__(128) knn_merge_rerank_kernel(const float* __restrict__ part_val,
                                                                const int* __restrict__ part_idx, int nparts, int cap,
                                                                const float* __restrict__ q, const float* __restrict__ xb,
@@ -248,22 +252,43 @@ __global__ void __launch_bounds__(128) knn_merge_rerank_kernel(const float* __re
   const int total = nparts * cap;
   const float* pv = part_val + static_cast<long long>(row) * total;
   const int* pi = part_idx + static_cast<long long>(row) * total;
-  // iterative selection: 32 rounds of warp arg-max with "already taken" tracked by last (value, id)
+  const bool in_regs = total <= 32 * kKnnMergePer;
+  float cv[kKnnMergePer];
+  int ci[kKnnMergePer];
+  if (in_regs) {
+#pragma unroll
+    for (int t = 0; t < kKnnMergePer; ++t) {
+      const int j = lane + 32 * t;
+      cv[t] = j < total ? pv[j] : -INFINITY;
+      ci[t] = j < total ? pi[j] : -1;
+    }
+  }
+  // iterative selection: `cap` rounds of warp arg-max with "already taken" tracked by last (value, id)
   float last_v = INFINITY;
   int last_i = -1;
   float my_v = -INFINITY;  // lane r ends up holding the r-th best candidate
   int my_i = -1;
-  for (int r = 0; r < kKnnCap; ++r) {
+  for (int r = 0; r < cap; ++r) {
     float bv = -INFINITY;
     int bi = 0x7fffffff;
-    for (int j = lane; j < total; j += 32) {
-      const float v = pv[j];
-      const int id = pi[j];
-      if (id < 0) continue;
-      // strictly after (last_v, last_i) in (value desc, id asc) order
-      const bool after = (v < last_v) || (v == last_v && id > last_i);
-      if (!after) continue;
-      if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; }
+    if (in_regs) {
+#pragma unroll
+      for (int t = 0; t < kKnnMergePer; ++t) {
+        const float v = cv[t];
+        const int id = ci[t];
+        // a live candidate strictly after (last_v, last_i) in (value desc, id asc) order that beats the running best
+        const bool after = id >= 0 && ((v < last_v) || (v == last_v && id > last_i));
+        if (after && (v > bv || (v == bv && id < bi))) { bv = v; bi = id; }
+      }
+    } else {
+      for (int j = lane; j < total; j += 32) {
+        const float v = pv[j];
+        const int id = pi[j];
+        if (id < 0) continue;
+        const bool after = (v < last_v) || (v == last_v && id > last_i);
+        if (!after) continue;
+        if (v > bv || (v == bv && id < bi)) { bv = v; bi = id; }
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -279,7 +304,7 @@ __global__ void __launch_bounds__(128) knn_merge_rerank_kernel(const float* __re
   // exact fp32 re-score, one candidate at a time, warp-cooperative dot product
   const float* qr = q + static_cast<long long>(row) * D;
   float exact = -INFINITY;
-  for (int c = 0; c < kKnnCap; ++c) {
+  for (int c = 0; c < cap; ++c) {
     const int id = __shfl_sync(0xffffffffu, my_i, c);
     if (id < 0) continue;
     const float* xr = xb + static_cast<long long>(id) * D;
@@ -291,7 +316,7 @@ __global__ void __launch_bounds__(128) knn_merge_rerank_kernel(const float* __re
   }
   // rank among the 32 by (exact desc, id asc)
   int rank = 0;
-  for (int c = 0; c < kKnnCap; ++c) {
+  for (int c = 0; c < cap; ++c) {
     const float ov = __shfl_sync(0xffffffffu, exact, c);
     const int oi = __shfl_sync(0xffffffffu, my_i, c);
     if (oi < 0 || c == lane) continue;
