@@ -148,6 +148,12 @@ static int launch_pair(const GemmArgs& a, cudaStream_t stream) {
   EpiTmaParams ep;
   ep.bias = a.bias;
   ep.gamma = a.gamma;
+  if (a.pos) {  // ViT patch embedding: row remap + position embedding in the epilogue
+    ep.pos = a.pos;
+    ep.x_out = reinterpret_cast<float*>(a.out);
+    ep.ldx = a.ldo;
+    ep.patches = a.patches;
+  }
   {
     KernelScope ks(a.prof_tag, stream);
     kern<<<2 * pairs, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, a.M, a.N, a.K, ep);
@@ -272,6 +278,9 @@ int gemm_f16(const GemmArgs& a, cudaStream_t stream) {
   if (a.pos) {
     if (a.N % 32 != 0 || a.patches <= 0 || !a.bias || !a.out_f32)
       return fail(EFFOCR_ERR_INVALID, "gemm: patch-embed epilogue needs N % 32 == 0, bias and fp32 output");
+    // large batches: CTA-pair kernel, the staged chunk leaves through coalesced remapped row copies (EpiTmaParams::pos)
+    if (use_pair(bn, a) && a.act == ACT_NONE && !a.gamma && !a.resid && a.epilogue != 1 && a.N % 4 == 0)
+      return bn == 192 ? launch_pair<192, ACT_NONE, true, false>(a, stream) : launch_pair<256, ACT_NONE, true, false>(a, stream);
     EpiPatchEmbed::Params ep;
     ep.x = reinterpret_cast<float*>(a.out);
     ep.bias = a.bias;

@@ -112,6 +112,13 @@ struct GemmTmaCfg {
 struct EpiTmaParams {
   const float* bias;   // [N] or nullptr
   const float* gamma;  // [N] or nullptr
+  // ViT patch embedding (fp32 output only): GEMM row m = image b, patch pi goes to row b * (patches + 1) + 1 + pi of
+  // x_out with pos[1 + pi] added.  The row remap is not a TMA box, so the staged chunk leaves through coalesced row
+  // copies (four full 128-byte rows per warp instruction) instead of the TMA store.  nullptr = ordinary output.
+  const float* pos = nullptr;
+  float* x_out = nullptr;
+  long long ldx = 0;
+  int patches = 0;
 };
 
 
@@ -121,7 +128,7 @@ __device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, cons
                                                   uint64_t* tfull_bar, uint64_t* tempty_bar, int as, uint32_t aphase,
                                                   int tile_m0, int tile_n0, int N, int q, int half, int lane,
                                                   uint8_t* stg, int warp_stg_bytes, int& buf,
-                                                  bool tempty_on_leader = false) {
+                                                  bool tempty_on_leader = false, int M_rows = 0x7fffffff) {
   constexpr int CHUNKS = BLOCK_N / 64;  // 32-column chunks per half
   const int m0 = tile_m0 + q * 32;
   const int n0 = tile_n0 + half * (BLOCK_N / 2);
@@ -192,6 +199,31 @@ __device__ __forceinline__ void tma_epilogue_tile(const CUtensorMap& tma_c, cons
 #pragma unroll
         for (int t = 0; t < 4; ++t) ph[t] = __floats2half2_rn(y[8 * j + 2 * t], y[8 * j + 2 * t + 1]);
         *reinterpret_cast<uint4*>(dst + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+      }
+    }
+    if constexpr (OUT_F32 && !REDUCE) {
+      if (ep.pos) {  // warp-uniform: remapped rows + position embedding, coalesced copies out of the staged chunk
+        __syncwarp();
+        const int piece = lane & 7;
+        int grow = m0 + (lane >> 3);              // GEMM row of this lane's first staged row
+        int b = grow / ep.patches;
+        int pi = grow - b * ep.patches;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3);
+          const float4 val = *reinterpret_cast<const float4*>(dst + r * 128 + ((piece ^ (r & 7)) << 4));
+          if (grow < M_rows && col0 + piece * 4 + 4 <= N) {
+            const float4 pp = __ldg(reinterpret_cast<const float4*>(ep.pos + static_cast<long long>(1 + pi) * N + col0 + piece * 4));
+            float* o = ep.x_out + (static_cast<long long>(b) * (ep.patches + 1) + 1 + pi) * ep.ldx + col0 + piece * 4;
+            *reinterpret_cast<float4*>(o) = make_float4(val.x + pp.x, val.y + pp.y, val.z + pp.z, val.w + pp.w);
+          }
+          grow += 4;
+          pi += 4;
+          if (pi >= ep.patches) { pi -= ep.patches; ++b; }
+        }
+        __syncwarp();  // the staging tile may be rewritten
+        buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+        continue;
       }
     }
     fence_proxy_async_smem();
@@ -713,7 +745,7 @@ gemm_tn_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_cons
       tma_epilogue_tile<BLOCK_N, ACT, OUT_F32, REDUCE>(tma_c, ep, tmem_base, tfull_bar, tempty_bar, as, aphase,
                                                         (tile / num_n) * 2 * kBlockM + rank * kBlockM,
                                                         (tile % num_n) * BLOCK_N, N, q, half, lane, stg,
-                                                        Cfg::kWarpStagingBytes, buf, /*tempty_on_leader=*/true);
+                                                        Cfg::kWarpStagingBytes, buf, /*tempty_on_leader=*/true, M);
     }
     if (lane == 0) tma_store_wait_all<0>();
   }
