@@ -22,8 +22,10 @@
 // passes are those of proj_ln_pair_kernel.  Warp roles (640 threads): warp 0 TMA producer (att, Wp, W1, W2), warp 1 MMA
 // issuer (leader CTA), warp 2 TMEM allocator, warp 3 residual-ring producer, warps 4-19 epilogue (TMEM lane quarter
 // w & 3, column group (w - 4) >> 2).
-// Numerics: identical to the two kernels except that fc2 accumulates ON TOP of x' in the fp32 TMEM accumulator instead of
-// being added to it afterwards (differences ~1e-6 relative, tests/test_gpu_blocks.py).
+// Numerics: the two kernels' arithmetic except that fc2 accumulates ON TOP of x' in the fp32 TMEM accumulator instead of
+// being added to it afterwards, and that the row sums of pass 1 are taken two lanes at a time (packed fp32x2), which flips
+// the fp16 rounding of an occasional h element: ~1e-5 relative on x per layer (tests/test_gpu_blocks.py), ~1e-4 on the
+// final embedding (tests/test_gpu_recognizer.py::test_three_kernel_layer_equals_separate_kernels), oracle bound 1e-3.
 #pragma once
 #include "mlp_sm100.cuh"
 #include "projln_sm100.cuh"
