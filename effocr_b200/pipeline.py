@@ -152,8 +152,18 @@ class RecognizerPipeline:
             up = upload(nxt) if nxt is not None else None  # next batch's upload is enqueued before this batch's kernels
             main.wait_event(ready)
             dist, idx, _ = self.recognize_device(pixels, images, boxes, n, k)
-            h_dist = torch.empty(dist.shape, dtype=dist.dtype, pin_memory=True)
-            h_idx = torch.empty(idx.shape, dtype=idx.dtype, pin_memory=True)
+            # results come back through a small ring of persistent pinned buffers: a fresh pinned allocation per batch
+            # goes through the caching host allocator, which falls back to cudaHostAlloc (milliseconds, device-wide
+            # synchronisation) whenever its event for a recycled block has not completed yet
+            ring = getattr(self, "_out_ring", None)
+            if ring is None or ring["k"] != k or ring["rows"] < dist.shape[0]:
+                rows = max(2 * int(dist.shape[0]), 1024)
+                ring = self._out_ring = {"k": k, "rows": rows, "next": 0,
+                                         "bufs": [(torch.empty((rows, k), dtype=dist.dtype, pin_memory=True),
+                                                   torch.empty((rows, k), dtype=idx.dtype, pin_memory=True)) for _ in range(3)]}
+            slot = ring["next"]
+            ring["next"] = (slot + 1) % 3
+            h_dist, h_idx = (t[:dist.shape[0]] for t in ring["bufs"][slot])
             h_dist.copy_(dist, non_blocking=True)
             h_idx.copy_(idx, non_blocking=True)
             ev = main.record_event()
@@ -162,11 +172,11 @@ class RecognizerPipeline:
             cur = (h_dist, h_idx, ev, (pixels, images, boxes, dist, idx))  # keep device buffers alive until consumed
             if pending is not None:
                 pending[2].synchronize()
-                yield pending[0].numpy(), pending[1].numpy()
+                yield pending[0].numpy().copy(), pending[1].numpy().copy()  # the ring slot is reused three batches later
             pending = cur
         if pending is not None:
             pending[2].synchronize()
-            yield pending[0].numpy(), pending[1].numpy()
+            yield pending[0].numpy().copy(), pending[1].numpy().copy()
 
     def recognize_crops(self, crops, k: int = 10):
         """crops: list of u8 [h, w, 3] arrays -> (distances [n,k], ids [n,k]) numpy."""
